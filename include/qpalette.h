@@ -1,0 +1,112 @@
+/* qpalette.h -- C ABI of libqpalette.so: B200 (sm_100a) kernels for Q-Palette's quantized-linear decode path.
+ *
+ * Every entry point takes raw DEVICE pointers, sizes and a CUDA stream (cudaStream_t passed as void*), never
+ * allocates, never synchronises, is CUDA-graph capturable, and returns QP_OK or a negative error code
+ * (qp_last_error() gives the message).  These are the functions the reference's pybind/torch FFI for this path
+ * would bind; each one cites the reference interface it replaces (paths relative to the Q-Palette repo).
+ * The `_host` variants take HOST buffers for the activations/result (weights stay device resident) and perform the
+ * host<->device copies on the given stream; they are what bench.py's `e2e` number goes through.
+ */
+#ifndef QPALETTE_H
+#define QPALETTE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QP_OK 0
+#define QP_ERR_ARG (-1)    /* bad shape / unsupported parameter combination */
+#define QP_ERR_CUDA (-2)   /* CUDA runtime error (launch, attribute, copy) */
+#define QP_ERR_ALIGN (-3)  /* pointer alignment requirement violated */
+
+/* split_mode for two-rate TCQ ("comb" quantizers) */
+#define QP_SPLIT_NONE 0
+#define QP_SPLIT_IN 1   /* tcomb_*: codes1 covers input columns [0,part1), codes2 the rest   (CombtLinearTCQ) */
+#define QP_SPLIT_OUT 2  /* comb_*:  codes1 covers output rows   [0,part1), codes2 the rest   (CombLinearTCQ)  */
+
+/* flags */
+#define QP_FLAG_ACCUMULATE 1u /* GEMV: add into `out` instead of overwriting it (out must hold valid fp32 data) */
+
+/* epilogue selector of qp_incoherent_* (fused layer ops) */
+#define QP_EPI_NONE 0
+#define QP_EPI_SILU_MUL 1 /* out[i] = silu(y[M/2 + i]) * y[i], i < M/2   (IncoherentMLP.compute_ug, merged up|gate) */
+
+int qp_version(void);
+const char *qp_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches claim) */
+uint64_t qp_launch_count(void);
+int qp_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * TCQ (bitshift trellis, L=16, V=2).  Packed layout = the `trellis` int16 buffer written by quantize_layer.py
+ * (lib/quantizer/tcq_quant.py:47-60).  S = tlut_bits in {9,10,11}, KV in 2..10 bits per weight pair.
+ * tlut: fp16 (2^S, 2).  x: fp16 (bs, K) row-major, bs <= 8.  out: fp32 (bs, M).
+ *
+ * Replaces tcq_kernels.decompress_gemm_16_{S}_{KV}_1_{M}_{N}_{K}, decompress_gemm_comb_*, decompress_gemm_combt_*
+ * (kernels/tcq-kernels/src/inference.cu:408-1218; python side lib/linear/__init__.py:176-250), shape-generic.
+ * For split modes codes2/KV2 describe the second part and part1 is its boundary (K1 or M1, multiple of 32/64).
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16,
+                int M, int K, int bs, int S, int KV1, int KV2, int split_mode, int part1, unsigned flags,
+                void *stream);
+
+/* Replaces tcq_kernels.decompress_16_{S}_{KV}, decompress_comb_*, decompress_combt_*
+ * (kernels/tcq-kernels/src/inference.cu:1222-1819; lib/linear/__init__.py:259-337).  W: fp16 (M, K) row-major. */
+int qp_tcq_dequant(void *W_f16, const void *codes1, const void *codes2, const void *tlut_f16, int M, int K, int S,
+                   int KV1, int KV2, int split_mode, int part1, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * VQ (vec_sz 2) / SQ (vec_sz 1) in the tensor-core layout (`qweight` int32 (M, bits*K/32/vec_sz),
+ * lib/quantizer/quant_op.py:101-162).  lut: fp16 (2^bits, vec_sz).  out: fp32 (bs, M), bs <= 8.
+ * Replaces vq_tensor_kernels.decompress_gemm_{bits}_{M}_{N}_{K}_{sq_dup|sq|vq2} and decompress_{bits}_{vtype}
+ * (kernels/vq-tensor-kernels/src/inference.cu:570-1108; lib/linear/__init__.py:43-117).
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_lut_gemv(float *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
+                int bits, int vec_sz, unsigned flags, void *stream);
+int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,
+                   void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * VQ / SQ in the SIMT layout (lib/quantizer/pack_op.py:288-335, quant_op.py:33-86).  out: fp16 (bs, M).
+ * Replaces sq_pack_gemm.pack_gemm / pack_dequant (kernels/sq-cuda-kernels/gemm_routines.cu:474-722) and
+ * vq_pack_gemm.vq_pack_gemm_* / vq_pack_dequant_* (kernels/vq-cuda-kernels/src/gemm_routines.cu:1913-2120).
+ * Accumulates in fp32 (the reference accumulates in fp16).
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_simt_gemv(void *out_f16, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
+                 int bits, int vec_sz, void *stream);
+int qp_simt_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,
+                    void *stream);
+/* GPU version of lib/quantizer/quant_op.py:246-257 convert_tensor_core_to_simt (format conversion at load time) */
+int qp_convert_tc_to_simt(void *simt_codes, const void *tc_codes, int M, int K, int bits, int vec_sz, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Incoherence processing.  y = ((hadK^T (x) H_{n/Kf}) (x * su)) * scale   along the last dim, Sylvester order;
+ * Kf in {1, 28} (hadK = the reference's get_had28, applied transposed as every inference call site does).
+ * Replaces hadamard::hadamard (lib/utils/matmul_had.py:124-134 -> fast_hadamard_transform) plus the dense
+ * `hadK @ .` of matmul_hadU_cuda / matmul_hadU_head_cuda (lib/utils/matmul_had.py:94-106,137-147) and the `x*SU`
+ * / `/scale` / `.half()` glue around them (lib/linear/incoherent_linear.py:82,106,325,336,491).
+ * x, y: (rows, n) with dtype selected by *_is_f32 (0 = fp16, 1 = fp32); su: fp16 (n,) or NULL.
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_hadamard(void *y, const void *x, const void *su_f16, int rows, int n, float scale, int x_is_f32,
+                int y_is_f32, void *stream);
+
+/* out (bs, M) fp16 = fp16(acc) * wscale * scale   [+ epilogue]; acc = fp32 (bs, M) GEMV result.
+ * The `.to(fp16) * Wscale * scale` (+ split + SiLU*mul) glue of lib/linear/incoherent_linear.py:83-108,326-338. */
+int qp_scale_epilogue(void *out_f16, const float *acc, const void *wscale_f16, int bs, int M, float scale,
+                      int epilogue, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * host-buffer variant used for end-to-end timing: x_host (bs,K) fp16 pinned/pageable host memory, out_host (bs,M)
+ * fp32 host memory; x_dev/out_dev are device scratch buffers of the same sizes.  Copies run on `stream`; the caller
+ * synchronises the stream before reading out_host.
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *codes1, const void *codes2, const void *x_host,
+                     void *x_dev, const void *tlut_f16, int M, int K, int bs, int S, int KV1, int KV2,
+                     int split_mode, int part1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPALETTE_H */

@@ -1,0 +1,75 @@
+"""Build libqpalette.so (sm_100a) in-tree with plain nvcc.  Used by __graft_entry__.build() and by hand:
+
+    python q-palette_b200/build.py [--force]
+
+The library is a C-ABI shared object (include/qpalette.h); it has no torch / pybind dependency, so it builds in
+about a minute and travels to the GPU box with the repo snapshot.
+"""
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "qpalette", "libqpalette.so")
+OBJ = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+         "--use_fast_math", "-Xptxas", "-v"]
+SOURCES = ["qp_api.cu", "tcq_kernels.cu", "lut_kernels.cu", "simt_kernels.cu", "had_kernels.cu", "decode_kernels.cu",
+           "gemm_tc_kernels.cu"]
+
+
+def _digest(path):
+    h = hashlib.sha1()
+    for name in sorted(os.listdir(CSRC)) + ["../../include/qpalette.h"]:
+        p = os.path.join(CSRC, name)
+        if os.path.isfile(p) and (name.endswith((".cuh", ".h")) or os.path.abspath(p) == os.path.abspath(path)):
+            h.update(open(p, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src):
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    stamp = obj + ".sha1"
+    d = _digest(path)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == d:
+        return obj, "", False
+    r = subprocess.run([NVCC, *FLAGS, "-c", path, "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    open(stamp, "w").write(d)
+    return obj, r.stderr, True
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(_compile, srcs))
+    objs = [r[0] for r in results]
+    if verbose:
+        for _, log, _ in results:
+            sys.stderr.write(log)
+    if any(r[2] for r in results) or not os.path.exists(OUT):
+        # cudart is linked statically (nvcc default): no dependency on a libcudart.so being on the loader path
+        r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+        for _, log, fresh in results:
+            if fresh:
+                f.write(log)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,245 @@
+// lut_kernels.cu -- fused LUT-decode + GEMV (bs <= 8) and dequantise kernels for Q-Palette's VQ (vec_sz 2) and SQ
+// (vec_sz 1) quantizers in the tensor-core packed layout (`qweight`, lib/quantizer/quant_op.py:101-162).
+// Replaces kernels/vq-tensor-kernels/src/inference.cu:570-1108 (vq2 / sq / sq_dup).  Same streaming skeleton as the TCQ
+// kernels (gemv_common.cuh); the decode is a plain table lookup:
+//   pair mode  : one lookup of the E-bit pair code in a 2^E-entry half2 table (vq2: the lut itself; SQ with R <= 5: the
+//                derived table {lut[c0], lut[c1]}, the reference's "sq_dup" idea extended to R = 5)
+//   split mode : SQ with R = 6..8: two lookups in the 2^R-entry table + one byte-permute.
+// Tables are lane-replicated in shared memory (slot = 2^SL bytes) so gathers are bank-conflict free up to E = 10; for
+// E = 11 / 12 only 16 / 8 copies fit in 128 KiB.
+#include "gemv_common.cuh"
+#include "lut_bits.cuh"
+
+namespace qp {
+
+template <int E, bool SPLIT>
+struct LutTable {
+    static constexpr int kR = E / 2;                                           // single-code bits (SQ)
+    static constexpr int kIndexBits = SPLIT ? kR : E;
+    static constexpr int kSL = (kIndexBits <= 10) ? 7 : (17 - kIndexBits);       // log2(slot bytes)
+    static constexpr int kEntries = 1 << kIndexBits;
+    static constexpr int kBytes = kEntries << kSL;
+    static constexpr uint32_t kLaneMask = (1u << (kSL - 2)) - 1u;
+};
+
+// r_single = 0: lut is (2^E, 2) fp16 (vq2).  r_single = R: lut is (2^R, 1) fp16 (SQ).
+template <int E, bool SPLIT>
+__device__ __forceinline__ void lut_build_table(uint32_t *tab, const void *__restrict__ lut, int r_single) {
+    using T = LutTable<E, SPLIT>;
+    constexpr int copies = 1 << (T::kSL - 2);
+    const uint32_t *lut32 = reinterpret_cast<const uint32_t *>(lut);
+    const uint16_t *lut16 = reinterpret_cast<const uint16_t *>(lut);
+    for (int i = threadIdx.x; i < T::kEntries * copies; i += blockDim.x) {
+        const int e = i / copies;
+        uint32_t v;
+        if (SPLIT) {
+            v = lut16[e];
+        } else if (r_single == 0) {
+            v = __ldg(lut32 + e);
+        } else {
+            const uint32_t lo = lut16[e & ((1 << r_single) - 1)], hi = lut16[e >> r_single];
+            v = lo | (hi << 16);
+        }
+        tab[i] = v;
+    }
+}
+
+template <int E, bool SPLIT>
+struct LutDecoder {
+    static constexpr int kE = E;
+    using T = LutTable<E, SPLIT>;
+
+    template <int TI, int J>
+    __device__ static __forceinline__ uint32_t one(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab) {
+        if constexpr (!SPLIT) {
+            return lds_u32(tab + lut_pair_offset<E, TI, J, T::kSL>(P));
+        } else {
+            const uint32_t w0 = lds_u32(tab + lut_single_offset<E, TI, J, 0, T::kSL>(P));
+            const uint32_t w1 = lds_u32(tab + lut_single_offset<E, TI, J, 1, T::kSL>(P));
+            return __byte_perm(w0, w1, 0x5410);
+        }
+    }
+    template <int TI>
+    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab, uint32_t (&f)[4]) {
+        f[0] = one<TI, 0>(P, tab);
+        f[1] = one<TI, 1>(P, tab);
+        f[2] = one<TI, 2>(P, tab);
+        f[3] = one<TI, 3>(P, tab);
+    }
+    __device__ static __forceinline__ void decode(const uint32_t (&raw)[TcqGeom<E>::kRawWords], int bitoff, int lane,
+                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
+        (void)lane;
+        uint32_t P[TcqGeom<E>::kWords];
+        tcq_align<E>(raw, bitoff, P);
+        tile<0>(P, tab_addr_lane, frag[0]);
+        tile<1>(P, tab_addr_lane, frag[1]);
+        tile<2>(P, tab_addr_lane, frag[2]);
+        tile<3>(P, tab_addr_lane, frag[3]);
+    }
+};
+
+template <int E, bool SPLIT>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+lut_gemv_kernel(PackSegment seg, float *__restrict__ out, const uint32_t *__restrict__ x32, const void *__restrict__ lut,
+                int r_single, int M, int K, int bs) {
+    using T = LutTable<E, SPLIT>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *xs = reinterpret_cast<uint32_t *>(smem + T::kBytes);
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * kGemvWarps;
+    const long TT = (long)seg.strips * seg.ksuper;
+    const long lo = TT * gwarp / nwarps, hi = TT * (gwarp + 1) / nwarps;
+    uint32_t raw[kGemvDepth][TcqGeom<E>::kRawWords];
+    gemv_prefetch<E>(seg, lo, hi, raw);
+    lut_build_table<E, SPLIT>(tab, lut, r_single);
+    pdl_wait();
+    stage_x(xs, x32, K, bs);
+    __syncthreads();
+    pdl_launch_dependents();
+    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & T::kLaneMask) << 2);
+    gemv_run_segment<LutDecoder<E, SPLIT>>(seg, out, M, bs, smem_u32(xs), tab_addr_lane, lo, hi, raw);
+}
+
+template <int E, bool SPLIT>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+lut_dequant_kernel(PackSegment seg, __half *__restrict__ W, const void *__restrict__ lut, int r_single, int K) {
+    using T = LutTable<E, SPLIT>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * kGemvWarps;
+    lut_build_table<E, SPLIT>(tab, lut, r_single);
+    __syncthreads();
+    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & T::kLaneMask) << 2);
+    dequant_run_segment<LutDecoder<E, SPLIT>>(seg, W, K, tab_addr_lane, gwarp, nwarps);
+}
+
+template <int E, bool SPLIT>
+static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const void *lut, int r_single, int M, int K,
+                           int bs, cudaStream_t st) {
+    using T = LutTable<E, SPLIT>;
+    auto kern = lut_gemv_kernel<E, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        configured = true;
+    }
+    const size_t smem = (size_t)T::kBytes + (size_t)K * bs * 2;
+    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg, out, (const uint32_t *)x, lut,
+                       r_single, M, K, bs));
+    return check_launch("lut_gemv");
+}
+
+template <int E, bool SPLIT>
+static int launch_lut_dequant(PackSegment seg, __half *W, const void *lut, int r_single, int K, cudaStream_t st) {
+    using T = LutTable<E, SPLIT>;
+    auto kern = lut_dequant_kernel<E, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        configured = true;
+    }
+    kern<<<sm_count(), kGemvThreads, T::kBytes, st>>>(seg, W, lut, r_single, K);
+    return check_launch("lut_dequant");
+}
+
+// smem bytes of the table for (bits, vec_sz); <0 if unsupported
+static int lut_table_bytes(int bits, int vec_sz) {
+    if (vec_sz == 2) {
+        if (bits < 2 || bits > 12) return -1;
+        return (1 << bits) << (bits <= 10 ? 7 : 17 - bits);
+    }
+    if (vec_sz == 1) {
+        if (bits < 2 || bits > 8) return -1;
+        return bits <= 5 ? ((1 << (2 * bits)) << 7) : ((1 << bits) << 7);
+    }
+    return -1;
+}
+
+#define QP_LUT_DISPATCH(FN, ...)                                                     \
+    if (vec_sz == 2) {                                                               \
+        switch (bits) {                                                              \
+            case 2: return FN<2, false>(__VA_ARGS__);                                \
+            case 3: return FN<3, false>(__VA_ARGS__);                                \
+            case 4: return FN<4, false>(__VA_ARGS__);                                \
+            case 5: return FN<5, false>(__VA_ARGS__);                                \
+            case 6: return FN<6, false>(__VA_ARGS__);                                \
+            case 7: return FN<7, false>(__VA_ARGS__);                                \
+            case 8: return FN<8, false>(__VA_ARGS__);                                \
+            case 9: return FN<9, false>(__VA_ARGS__);                                \
+            case 10: return FN<10, false>(__VA_ARGS__);                              \
+            case 11: return FN<11, false>(__VA_ARGS__);                              \
+            case 12: return FN<12, false>(__VA_ARGS__);                              \
+        }                                                                            \
+    } else {                                                                         \
+        switch (bits) {                                                              \
+            case 2: return FN<4, false>(__VA_ARGS__);                                \
+            case 3: return FN<6, false>(__VA_ARGS__);                                \
+            case 4: return FN<8, false>(__VA_ARGS__);                                \
+            case 5: return FN<10, false>(__VA_ARGS__);                               \
+            case 6: return FN<12, true>(__VA_ARGS__);                                \
+            case 7: return FN<14, true>(__VA_ARGS__);                                \
+            case 8: return FN<16, true>(__VA_ARGS__);                                \
+        }                                                                            \
+    }
+
+static int dispatch_lut_gemv(int bits, int vec_sz, PackSegment seg, float *out, const void *x, const void *lut, int M,
+                             int K, int bs, cudaStream_t st) {
+    const int r_single = vec_sz == 1 ? bits : 0;
+    QP_LUT_DISPATCH(launch_lut_gemv, seg, out, x, lut, r_single, M, K, bs, st)
+    return fail(QP_ERR_ARG, "unsupported LUT configuration bits=%d vec_sz=%d", bits, vec_sz);
+}
+
+static int dispatch_lut_dequant(int bits, int vec_sz, PackSegment seg, __half *W, const void *lut, int K,
+                                cudaStream_t st) {
+    const int r_single = vec_sz == 1 ? bits : 0;
+    QP_LUT_DISPATCH(launch_lut_dequant, seg, W, lut, r_single, K, st)
+    return fail(QP_ERR_ARG, "unsupported LUT configuration bits=%d vec_sz=%d", bits, vec_sz);
+}
+
+}  // namespace qp
+
+using namespace qp;
+
+static int lut_check(const void *codes, int M, int K, int bits, int vec_sz) {
+    QP_CHECK_ARG(codes != nullptr, "codes is NULL");
+    QP_CHECK_ARG(vec_sz == 1 || vec_sz == 2, "tensor-core layout supports vec_sz 1 or 2 (got %d)", vec_sz);
+    QP_CHECK_ARG(lut_table_bytes(bits, vec_sz) > 0, "unsupported bits=%d for vec_sz=%d", bits, vec_sz);
+    QP_CHECK_ARG(M > 0 && K > 0 && M % 32 == 0 && K % 32 == 0, "needs M %% 32 == 0 and K %% 32 == 0 (got %d x %d)", M, K);
+    return check_align(codes, 16, "codes");
+}
+
+extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
+                           int bits, int vec_sz, unsigned flags, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out && x_f16 && lut_f16, "NULL pointer argument");
+    QP_CHECK_ARG(bs >= 1 && bs <= 8, "bs = %d: the fused GEMV handles 1..8 rows", bs);
+    int rc = lut_check(codes, M, K, bits, vec_sz);
+    if (rc != QP_OK) return rc;
+    const size_t avail = (size_t)kMaxSmem - (size_t)lut_table_bytes(bits, vec_sz);
+    int chunk = (int)(avail / ((size_t)K * 2));
+    QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
+    if (chunk > bs) chunk = bs;
+    if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
+    PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
+    for (int b0 = 0; b0 < bs; b0 += chunk) {
+        const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
+        rc = dispatch_lut_gemv(bits, vec_sz, seg, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, lut_f16,
+                               M, K, nb, st);
+        if (rc != QP_OK) return rc;
+    }
+    return QP_OK;
+}
+
+extern "C" int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,
+                              void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(W_f16 && lut_f16, "NULL pointer argument");
+    int rc = lut_check(codes, M, K, bits, vec_sz);
+    if (rc != QP_OK) return rc;
+    PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
+    return dispatch_lut_dequant(bits, vec_sz, seg, (__half *)W_f16, lut_f16, K, st);
+}

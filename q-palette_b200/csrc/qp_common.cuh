@@ -1,0 +1,104 @@
+// qp_common.cuh -- shared host/device helpers for libqpalette.so (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/qpalette.h"
+
+namespace qp {
+
+constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+char *last_error_buf();                       // thread-local, 512 bytes
+int fail(int code, const char *fmt, ...);     // formats into last_error_buf and returns code
+extern std::atomic<uint64_t> g_launches;      // kernels launched by this library
+int sm_count();                               // cached cudaDevAttrMultiProcessorCount of the current device
+
+#define QP_CHECK_ARG(cond, ...)                                  \
+    do {                                                         \
+        if (!(cond)) return ::qp::fail(QP_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+#define QP_CUDA(expr)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return ::qp::fail(QP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QP_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return QP_OK;
+}
+
+// launch with the programmatic-dependent-launch attribute so the kernel's weight-independent prologue (codebook
+// build, first weight prefetch) overlaps the tail of the previous kernel on the stream.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- device side -------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// streaming loads of packed codes: read exactly once per launch
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::evict_first.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream_u64(const uint32_t *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream_u128(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+#endif
+
+}  // namespace qp

@@ -1,0 +1,353 @@
+// tcq_kernels.cu -- fused trellis-decode + GEMV (bs <= 8) and dequantise kernels for Q-Palette's TCQ quantizers.
+//
+// What is computed (reference: kernels/tcq-kernels/src/inference.cu:408-1819, format lib/quantizer/tcq_quant.py:47-60):
+//   out[n][m] (+)= sum_k decode(W)[m][k] * x[n][k]
+// Design (B200): one persistent CTA per SM, 16 warps.  The packed matrix is a flat array of 32x32 super-tiles
+// (64*KV contiguous bytes each, [M/32][K/32] order); every warp owns one contiguous run of super-tiles, so the whole
+// grid streams the buffer exactly once with contiguous per-warp reads and an (almost) perfectly even split whatever
+// M and K are.  Per super-tile a lane: loads its 16*KV payload bits straight into registers (prefetched kDepth
+// super-tiles ahead), exchanges chunk tops with lane+1 by shuffle (tail-biting trellis), forms 16 states, hashes
+// them (s*(s+1)), looks the fp16 pairs up in a lane-replicated shared-memory codebook (bank = lane -> conflict-free)
+// and feeds them as the A fragment of mma.m16n8k16 with x as the B fragment (fp32 accumulate).  Partial sums of a
+// 32-row strip are added to `out` with fp32 atomics when the run leaves the strip.
+// The decode is ALU/issue-bound on B200 (HBM bytes per SM-clock are 7x an RTX 4090's), so the inner loop is written
+// to minimise issued instructions per weight pair: see DESIGN.md "TCQ GEMV instruction budget".
+#include "qp_common.cuh"
+#include "tcq_bits.cuh"
+#include "gemv_common.cuh"
+
+namespace qp {
+
+constexpr int kTcqThreads = kGemvThreads;
+constexpr int kTcqWarps = kGemvWarps;
+
+// ---- lane-replicated codebook in shared memory ---------------------------------------------------------------------
+// entry slot = 2^kStrideLog2 bytes = one 4-byte copy per lane (or per lane pair for S = 11), so a warp-wide gather never
+// has two lanes in the same bank with different addresses.  For S = 9 the sign flip (bit 15 of the hash) is folded into
+// the table (2^10 entries) which saves the XOR in the inner loop; S = 10/11 keep the XOR (table would not fit).
+template <int S>
+struct TcqTable {
+    static_assert(S >= 9 && S <= 11, "tlut_bits must be 9, 10 or 11");
+    static constexpr bool kFold = (S == 9);
+    static constexpr int kStrideLog2 = (S == 11) ? 6 : 7;
+    static constexpr int kEntryBits = S + (kFold ? 1 : 0);
+    static constexpr int kEntries = 1 << kEntryBits;
+    static constexpr int kBytes = kEntries << kStrideLog2;            // 128 KiB for all three
+    static constexpr int kShift = kStrideLog2 - (15 - S);             // hash bit (15-S) -> address bit kStrideLog2
+    static constexpr uint32_t kMask = (uint32_t)(kEntries - 1) << kStrideLog2;
+    static constexpr uint32_t kLaneMask = (1u << (kStrideLog2 - 2)) - 1u;
+};
+
+template <int S>
+__device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *__restrict__ tlut) {
+    using T = TcqTable<S>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (T::kStrideLog2 == 7) {
+        for (int e = warp; e < T::kEntries; e += kTcqWarps) {
+            uint32_t v = __ldg(tlut + (e & ((1 << S) - 1)));
+            if (T::kFold && (e >> S)) v ^= 0x8000u;  // negate component 0 (low half)
+            tab[e * 32 + lane] = v;
+        }
+    } else {  // 16 copies per entry: one warp store covers two entries
+        for (int e2 = warp; e2 < T::kEntries / 2; e2 += kTcqWarps) {
+            const int e = e2 * 2 + (lane >> 4);
+            tab[e * 16 + (lane & 15)] = __ldg(tlut + e);
+        }
+    }
+}
+
+template <int S>
+__device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_addr_lane, uint32_t u) {
+    using T = TcqTable<S>;
+    const uint32_t t = tcq_hash(u);
+    uint32_t w = lds_u32(tab_addr_lane + ((t << T::kShift) & T::kMask));
+    if (!T::kFold) w ^= (t & 0x8000u);
+    return w;
+}
+
+// decode the 16 fp16 pairs of one (lane, super-tile): frag[t][j] = A-fragment register j of tile t = kl*2+ml
+template <int KV, int S>
+struct TcqDecoder {
+    static constexpr int kE = KV;
+    __device__ static __forceinline__ void decode(const uint32_t (&raw)[TcqGeom<KV>::kRawWords], int bitoff, int lane,
+                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
+        using G = TcqGeom<KV>;
+        uint32_t P[G::kWords];
+        tcq_align<KV>(raw, bitoff, P);
+        uint32_t send[4] = {tcq_send<KV, 0>(P), tcq_send<KV, 1>(P), tcq_send<KV, 2>(P), tcq_send<KV, 3>(P)};
+        uint32_t n1[4], n2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            n1[t] = __shfl_sync(0xffffffffu, send[t], (lane + 1) & 31);
+            n2[t] = (G::kNeighbors == 2) ? __shfl_sync(0xffffffffu, send[t], (lane + 2) & 31) : 0u;
+        }
+        uint32_t u[4][4];
+        tcq_states<KV, 0>(P, n1[0], n2[0], u[0]);
+        tcq_states<KV, 1>(P, n1[1], n2[1], u[1]);
+        tcq_states<KV, 2>(P, n1[2], n2[2], u[2]);
+        tcq_states<KV, 3>(P, n1[3], n2[3], u[3]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) frag[t][j] = tcq_lookup<S>(tab_addr_lane, u[t][j]);
+    }
+};
+
+using TcqSegment = PackSegment;
+
+// ---- GEMV -----------------------------------------------------------------------------------------------------------
+template <int KVA, int KVB, int S>
+__global__ void __launch_bounds__(kTcqThreads, 1)
+tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, float *__restrict__ out, const uint32_t *__restrict__ x32,
+                const uint32_t *__restrict__ tlut, int M, int K, int bs) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *xs = reinterpret_cast<uint32_t *>(smem + TcqTable<S>::kBytes);
+
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kTcqWarps + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * kTcqWarps;
+
+    // even split of each part's super-tiles over all warps of the grid
+    const long TA = (long)segA.strips * segA.ksuper;
+    const long loA = TA * gwarp / nwarps, hiA = TA * (gwarp + 1) / nwarps;
+    uint32_t rawA[kGemvDepth][TcqGeom<KVA>::kRawWords];
+    gemv_prefetch<KVA>(segA, loA, hiA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
+
+    tcq_build_table<S>(tab, tlut);
+    pdl_wait();  // x (and out) are produced by the preceding kernel
+    stage_x(xs, x32, K, bs);
+    __syncthreads();
+    pdl_launch_dependents();
+
+    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & TcqTable<S>::kLaneMask) << 2);
+    const uint32_t xs_addr = smem_u32(xs);
+    gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, loA, hiA, rawA);
+    if constexpr (KVB != 0) {
+        const long TB = (long)segB.strips * segB.ksuper;
+        const long loB = TB * gwarp / nwarps, hiB = TB * (gwarp + 1) / nwarps;
+        uint32_t rawB[kGemvDepth][TcqGeom<KVB>::kRawWords];
+        gemv_prefetch<KVB>(segB, loB, hiB, rawB);
+        gemv_run_segment<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, loB, hiB, rawB);
+    }
+}
+
+// ---- dequantise -----------------------------------------------------------------------------------------------------
+template <int KVA, int KVB, int S>
+__global__ void __launch_bounds__(kTcqThreads, 1)
+tcq_dequant_kernel(TcqSegment segA, TcqSegment segB, __half *__restrict__ W, const uint32_t *__restrict__ tlut, int K) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kTcqWarps + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * kTcqWarps;
+    tcq_build_table<S>(tab, tlut);
+    __syncthreads();
+    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & TcqTable<S>::kLaneMask) << 2);
+    dequant_run_segment<TcqDecoder<KVA, S>>(segA, W, K, tab_addr_lane, gwarp, nwarps);
+    if constexpr (KVB != 0) dequant_run_segment<TcqDecoder<KVB, S>>(segB, W, K, tab_addr_lane, gwarp, nwarps);
+}
+
+// ---- host dispatch --------------------------------------------------------------------------------------------------
+struct TcqLaunch {
+    TcqSegment a, b;
+    int kva, kvb;
+};
+
+static int make_segments(TcqLaunch &L, const void *codes1, const void *codes2, int M, int K, int KV1, int KV2,
+                         int split_mode, int part1) {
+    QP_CHECK_ARG(M > 0 && K > 0 && M % 32 == 0 && K % 32 == 0, "TCQ needs M %% 32 == 0 and K %% 32 == 0 (got %d x %d)", M, K);
+    QP_CHECK_ARG(codes1 != nullptr, "codes1 is NULL");
+    QP_CHECK_ARG(KV1 >= 2 && KV1 <= 10, "KV1 = %d out of range 2..10", KV1);
+    if (split_mode == QP_SPLIT_NONE) {
+        L.a = TcqSegment{(const uint32_t *)codes1, M / 32, K / 32, 0, 0};
+        L.b = TcqSegment{nullptr, 0, 0, 0, 0};
+        L.kva = KV1;
+        L.kvb = 0;
+        return QP_OK;
+    }
+    QP_CHECK_ARG(codes2 != nullptr, "codes2 is NULL for a two-rate layer");
+    QP_CHECK_ARG(KV2 >= 2 && KV2 <= 10, "KV2 = %d out of range 2..10", KV2);
+    if (split_mode == QP_SPLIT_IN) {
+        QP_CHECK_ARG(part1 > 0 && part1 < K && part1 % 32 == 0, "in_part boundary %d must be a multiple of 32 inside (0,%d)", part1, K);
+        L.a = TcqSegment{(const uint32_t *)codes1, M / 32, part1 / 32, 0, 0};
+        L.b = TcqSegment{(const uint32_t *)codes2, M / 32, (K - part1) / 32, 0, part1 / 32};
+    } else if (split_mode == QP_SPLIT_OUT) {
+        QP_CHECK_ARG(part1 > 0 && part1 < M && part1 % 32 == 0, "out_part boundary %d must be a multiple of 32 inside (0,%d)", part1, M);
+        L.a = TcqSegment{(const uint32_t *)codes1, part1 / 32, K / 32, 0, 0};
+        L.b = TcqSegment{(const uint32_t *)codes2, (M - part1) / 32, K / 32, part1, 0};
+    } else {
+        return fail(QP_ERR_ARG, "unknown split_mode %d", split_mode);
+    }
+    L.kva = KV1;
+    L.kvb = KV2;
+    return QP_OK;
+}
+
+template <int KVA, int KVB, int S>
+static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void *tlut, int M, int K, int bs,
+                       cudaStream_t st) {
+    auto kern = tcq_gemv_kernel<KVA, KVB, S>;
+    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        configured = true;
+    }
+    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kTcqThreads), smem, st, L.a, L.b, out, (const uint32_t *)x,
+                       (const uint32_t *)tlut, M, K, bs));
+    return check_launch("tcq_gemv");
+}
+
+template <int KVA, int KVB, int S>
+static int launch_dequant(const TcqLaunch &L, __half *W, const void *tlut, int K, cudaStream_t st) {
+    auto kern = tcq_dequant_kernel<KVA, KVB, S>;
+    static bool configured = false;
+    if (!configured) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        configured = true;
+    }
+    kern<<<sm_count(), kTcqThreads, TcqTable<S>::kBytes, st>>>(L.a, L.b, W, (const uint32_t *)tlut, K);
+    return check_launch("tcq_dequant");
+}
+
+// (KV1, KV2, S) combinations: every single rate 2..10 with any S in {9,10,11}; two-rate pairs (a, a+1) as the reference
+// registers them (lib/linear/__init__.py:166-250) plus the reversed and equal-rate pairs are reachable through the
+// generic two-launch fallback below.
+#define QP_TCQ_SINGLE(FN, KV, ...)                                          \
+    switch (S) {                                                            \
+        case 9: return FN<KV, 0, 9>(__VA_ARGS__);                           \
+        case 10: return FN<KV, 0, 10>(__VA_ARGS__);                         \
+        case 11: return FN<KV, 0, 11>(__VA_ARGS__);                         \
+    }                                                                       \
+    break;
+
+#define QP_TCQ_PAIR(FN, KA, ...)                                            \
+    switch (S) {                                                            \
+        case 9: return FN<KA, KA + 1, 9>(__VA_ARGS__);                      \
+        case 10: return FN<KA, KA + 1, 10>(__VA_ARGS__);                    \
+        case 11: return FN<KA, KA + 1, 11>(__VA_ARGS__);                    \
+    }                                                                       \
+    break;
+
+static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, const void *tlut, int M, int K, int bs,
+                         cudaStream_t st) {
+    if (L.kvb == 0) {
+        switch (L.kva) {
+            case 2: QP_TCQ_SINGLE(launch_gemv, 2, L, out, x, tlut, M, K, bs, st)
+            case 3: QP_TCQ_SINGLE(launch_gemv, 3, L, out, x, tlut, M, K, bs, st)
+            case 4: QP_TCQ_SINGLE(launch_gemv, 4, L, out, x, tlut, M, K, bs, st)
+            case 5: QP_TCQ_SINGLE(launch_gemv, 5, L, out, x, tlut, M, K, bs, st)
+            case 6: QP_TCQ_SINGLE(launch_gemv, 6, L, out, x, tlut, M, K, bs, st)
+            case 7: QP_TCQ_SINGLE(launch_gemv, 7, L, out, x, tlut, M, K, bs, st)
+            case 8: QP_TCQ_SINGLE(launch_gemv, 8, L, out, x, tlut, M, K, bs, st)
+            case 9: QP_TCQ_SINGLE(launch_gemv, 9, L, out, x, tlut, M, K, bs, st)
+            case 10: QP_TCQ_SINGLE(launch_gemv, 10, L, out, x, tlut, M, K, bs, st)
+        }
+    } else if (L.kvb == L.kva + 1) {
+        switch (L.kva) {
+            case 2: QP_TCQ_PAIR(launch_gemv, 2, L, out, x, tlut, M, K, bs, st)
+            case 3: QP_TCQ_PAIR(launch_gemv, 3, L, out, x, tlut, M, K, bs, st)
+            case 4: QP_TCQ_PAIR(launch_gemv, 4, L, out, x, tlut, M, K, bs, st)
+            case 5: QP_TCQ_PAIR(launch_gemv, 5, L, out, x, tlut, M, K, bs, st)
+            case 6: QP_TCQ_PAIR(launch_gemv, 6, L, out, x, tlut, M, K, bs, st)
+            case 7: QP_TCQ_PAIR(launch_gemv, 7, L, out, x, tlut, M, K, bs, st)
+            case 8: QP_TCQ_PAIR(launch_gemv, 8, L, out, x, tlut, M, K, bs, st)
+            case 9: QP_TCQ_PAIR(launch_gemv, 9, L, out, x, tlut, M, K, bs, st)
+        }
+    } else {
+        // arbitrary pair: two single-rate launches accumulating into the same output
+        TcqLaunch a = L, b = L;
+        a.kvb = 0;
+        b.a = L.b;
+        b.kva = L.kvb;
+        b.kvb = 0;
+        int rc = dispatch_gemv(a, S, out, x, tlut, M, K, bs, st);
+        if (rc != QP_OK) return rc;
+        return dispatch_gemv(b, S, out, x, tlut, M, K, bs, st);
+    }
+    return fail(QP_ERR_ARG, "unsupported TCQ configuration S=%d KV=(%d,%d)", S, L.kva, L.kvb);
+}
+
+static int dispatch_dequant(const TcqLaunch &L, int S, __half *W, const void *tlut, int K, cudaStream_t st) {
+    if (L.kvb == 0) {
+        switch (L.kva) {
+            case 2: QP_TCQ_SINGLE(launch_dequant, 2, L, W, tlut, K, st)
+            case 3: QP_TCQ_SINGLE(launch_dequant, 3, L, W, tlut, K, st)
+            case 4: QP_TCQ_SINGLE(launch_dequant, 4, L, W, tlut, K, st)
+            case 5: QP_TCQ_SINGLE(launch_dequant, 5, L, W, tlut, K, st)
+            case 6: QP_TCQ_SINGLE(launch_dequant, 6, L, W, tlut, K, st)
+            case 7: QP_TCQ_SINGLE(launch_dequant, 7, L, W, tlut, K, st)
+            case 8: QP_TCQ_SINGLE(launch_dequant, 8, L, W, tlut, K, st)
+            case 9: QP_TCQ_SINGLE(launch_dequant, 9, L, W, tlut, K, st)
+            case 10: QP_TCQ_SINGLE(launch_dequant, 10, L, W, tlut, K, st)
+        }
+    } else {
+        TcqLaunch a = L, b = L;
+        a.kvb = 0;
+        b.a = L.b;
+        b.kva = L.kvb;
+        b.kvb = 0;
+        int rc = dispatch_dequant(a, S, W, tlut, K, st);
+        if (rc != QP_OK) return rc;
+        return dispatch_dequant(b, S, W, tlut, K, st);
+    }
+    return fail(QP_ERR_ARG, "unsupported TCQ configuration S=%d KV=(%d,%d)", S, L.kva, L.kvb);
+}
+
+}  // namespace qp
+
+using namespace qp;
+
+extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16,
+                           int M, int K, int bs, int S, int KV1, int KV2, int split_mode, int part1, unsigned flags,
+                           void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out && x_f16 && tlut_f16, "NULL pointer argument");
+    QP_CHECK_ARG(bs >= 1 && bs <= 8, "bs = %d: the fused GEMV handles 1..8 rows (use the dequant + GEMM path above)", bs);
+    QP_CHECK_ARG(S >= 9 && S <= 11, "tlut_bits S = %d not in {9,10,11}", S);
+    TcqLaunch L;
+    int rc = make_segments(L, codes1, codes2, M, K, KV1, KV2, split_mode, part1);
+    if (rc != QP_OK) return rc;
+    if ((rc = check_align(codes1, 16, "codes1")) != QP_OK) return rc;
+    if (codes2 && (rc = check_align(codes2, 16, "codes2")) != QP_OK) return rc;
+    if ((rc = check_align(x_f16, 4, "x")) != QP_OK) return rc;
+    if ((rc = check_align(tlut_f16, 4, "tlut")) != QP_OK) return rc;
+    // x lives in shared memory next to the 128 KiB codebook: process the batch in chunks that fit
+    const size_t avail = (size_t)kMaxSmem - 128 * 1024;
+    int chunk = (int)(avail / ((size_t)K * 2));
+    QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
+    if (chunk > bs) chunk = bs;
+    if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
+    for (int b0 = 0; b0 < bs; b0 += chunk) {
+        const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
+        rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, st);
+        if (rc != QP_OK) return rc;
+    }
+    return QP_OK;
+}
+
+extern "C" int qp_tcq_dequant(void *W_f16, const void *codes1, const void *codes2, const void *tlut_f16, int M, int K,
+                              int S, int KV1, int KV2, int split_mode, int part1, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(W_f16 && tlut_f16, "NULL pointer argument");
+    QP_CHECK_ARG(S >= 9 && S <= 11, "tlut_bits S = %d not in {9,10,11}", S);
+    TcqLaunch L;
+    int rc = make_segments(L, codes1, codes2, M, K, KV1, KV2, split_mode, part1);
+    if (rc != QP_OK) return rc;
+    if ((rc = check_align(codes1, 16, "codes1")) != QP_OK) return rc;
+    if (codes2 && (rc = check_align(codes2, 16, "codes2")) != QP_OK) return rc;
+    return dispatch_dequant(L, S, (__half *)W_f16, tlut_f16, K, st);
+}
+
+extern "C" int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *codes1, const void *codes2,
+                                const void *x_host, void *x_dev, const void *tlut_f16, int M, int K, int bs, int S,
+                                int KV1, int KV2, int split_mode, int part1, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out_host && out_dev && x_host && x_dev, "NULL pointer argument");
+    QP_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)bs * K * 2, cudaMemcpyHostToDevice, st));
+    int rc = qp_tcq_gemv(out_dev, codes1, codes2, x_dev, tlut_f16, M, K, bs, S, KV1, KV2, split_mode, part1, 0, stream);
+    if (rc != QP_OK) return rc;
+    QP_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)bs * M * 4, cudaMemcpyDeviceToHost, st));
+    return QP_OK;
+}

@@ -1,0 +1,65 @@
+"""ctypes binding of libqpalette.so (include/qpalette.h).  There is no fallback: if the library is missing or a call
+fails this raises, so a GPU test can never silently pass on a CPU / eager path."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpalette.so")
+
+QP_OK = 0
+SPLIT_NONE, SPLIT_IN, SPLIT_OUT = 0, 1, 2
+FLAG_ACCUMULATE = 1
+EPI_NONE, EPI_SILU_MUL = 0, 1
+
+_lib = None
+
+_vp, _i, _u, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_float
+
+# name -> argtypes  (restype is int unless listed in _RESTYPES); must mirror include/qpalette.h
+SIGNATURES = {
+    "qp_version": [],
+    "qp_last_error": [],
+    "qp_launch_count": [],
+    "qp_device_sm_count": [],
+    "qp_tcq_gemv": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
+    "qp_tcq_dequant": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "qp_lut_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
+    "qp_lut_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "qp_simt_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "qp_simt_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "qp_convert_tc_to_simt": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "qp_hadamard": [_vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
+    "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "qp_tcq_gemv_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+}
+_RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64}
+
+
+class QPaletteError(RuntimeError):
+    pass
+
+
+def lib():
+    """load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QPaletteError(
+                f"{LIB_PATH} not found: build it with `python q-palette_b200/build.py` (there is no CPU fallback)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is missing
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != QP_OK:
+        msg = lib().qp_last_error()
+        raise QPaletteError(f"libqpalette error {rc}: {msg.decode() if msg else '?'}")
+
+
+def launch_count():
+    return int(lib().qp_launch_count())
