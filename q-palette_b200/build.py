@@ -18,6 +18,13 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
          "--use_fast_math", "-Xptxas", "-v"]
+# tuning knobs of the streaming GEMV kernels (see csrc/gemv_common.cuh); override for experiments
+for _k in ("QP_GEMV_THREADS", "QP_GEMV_DEPTH", "QP_PROFILE_PHASES"):
+    if os.environ.get(_k):
+        FLAGS.append(f"-D{_k}={os.environ[_k]}")
+if os.environ.get("QP_LIB_SUFFIX"):
+    OUT = OUT.replace("libqpalette.so", f"libqpalette{os.environ['QP_LIB_SUFFIX']}.so")
+    OBJ = OBJ + os.environ["QP_LIB_SUFFIX"]
 SOURCES = ["qp_api.cu", "tcq_kernels.cu", "lut_kernels.cu", "simt_kernels.cu", "had_kernels.cu", "decode_kernels.cu",
            "gemm_tc_kernels.cu"]
 

@@ -22,25 +22,27 @@ struct LutTable {
     static constexpr uint32_t kLaneMask = (1u << (kSL - 2)) - 1u;
 };
 
-// r_single = 0: lut is (2^E, 2) fp16 (vq2).  r_single = R: lut is (2^R, 1) fp16 (SQ).
+// compact lut copy size in 32-bit words.  r_single = 0: lut is (2^E, 2) fp16 (vq2).  r_single = R: lut is (2^R, 1) fp16.
+__host__ __device__ inline int lut_copy_words(int E, int r_single) { return r_single ? ((1 << r_single) / 2) : (1 << E); }
+// ... rounded up so the x stage behind it stays 16-byte aligned
+__host__ __device__ inline int lut_compact_words(int E, int r_single) { return (lut_copy_words(E, r_single) + 3) & ~3; }
+
+// expand the compact lut copy (shared memory) into the lane-replicated table
 template <int E, bool SPLIT>
-__device__ __forceinline__ void lut_build_table(uint32_t *tab, const void *__restrict__ lut, int r_single) {
+__device__ __forceinline__ void lut_build_table(uint32_t *tab, const uint32_t *lc, int r_single) {
     using T = LutTable<E, SPLIT>;
-    constexpr int copies = 1 << (T::kSL - 2);
-    const uint32_t *lut32 = reinterpret_cast<const uint32_t *>(lut);
-    const uint16_t *lut16 = reinterpret_cast<const uint16_t *>(lut);
-    for (int i = threadIdx.x; i < T::kEntries * copies; i += blockDim.x) {
-        const int e = i / copies;
-        uint32_t v;
-        if (SPLIT) {
-            v = lut16[e];
-        } else if (r_single == 0) {
-            v = __ldg(lut32 + e);
-        } else {
-            const uint32_t lo = lut16[e & ((1 << r_single) - 1)], hi = lut16[e >> r_single];
-            v = lo | (hi << 16);
-        }
-        tab[i] = v;
+    const uint16_t *lut16 = reinterpret_cast<const uint16_t *>(lc);
+    auto value = [&](int e) -> uint32_t {
+        if (SPLIT) return lut16[e];
+        if (r_single == 0) return lc[e];
+        const uint32_t lo = lut16[e & ((1 << r_single) - 1)], hi = lut16[e >> r_single];
+        return lo | (hi << 16);
+    };
+    if constexpr (T::kSL == 7) {
+        fill_replicated_128(tab, T::kEntries, value);
+    } else {
+        constexpr int copies = 1 << (T::kSL - 2);
+        for (int i = threadIdx.x; i < T::kEntries * copies; i += blockDim.x) tab[i] = value(i / copies);
     }
 }
 
@@ -50,27 +52,25 @@ struct LutDecoder {
     using T = LutTable<E, SPLIT>;
 
     template <int TI, int J>
-    __device__ static __forceinline__ uint32_t one(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab) {
+    __device__ static __forceinline__ uint32_t one(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab) {
         if constexpr (!SPLIT) {
-            return lds_u32(tab + lut_pair_offset<E, TI, J, T::kSL>(P));
+            return *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, J, T::kSL>(P));
         } else {
-            const uint32_t w0 = lds_u32(tab + lut_single_offset<E, TI, J, 0, T::kSL>(P));
-            const uint32_t w1 = lds_u32(tab + lut_single_offset<E, TI, J, 1, T::kSL>(P));
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tab + lut_single_offset<E, TI, J, 0, T::kSL>(P));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tab + lut_single_offset<E, TI, J, 1, T::kSL>(P));
             return __byte_perm(w0, w1, 0x5410);
         }
     }
     template <int TI>
-    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab, uint32_t (&f)[4]) {
+    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab, uint32_t (&f)[4]) {
         f[0] = one<TI, 0>(P, tab);
         f[1] = one<TI, 1>(P, tab);
         f[2] = one<TI, 2>(P, tab);
         f[3] = one<TI, 3>(P, tab);
     }
-    __device__ static __forceinline__ void decode(const uint32_t (&raw)[TcqGeom<E>::kRawWords], int bitoff, int lane,
-                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
+    __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<E>::kWords], int lane,
+                                                  const uint8_t *tab_addr_lane, uint32_t (&frag)[4][4]) {
         (void)lane;
-        uint32_t P[TcqGeom<E>::kWords];
-        tcq_align<E>(raw, bitoff, P);
         tile<0>(P, tab_addr_lane, frag[0]);
         tile<1>(P, tab_addr_lane, frag[1]);
         tile<2>(P, tab_addr_lane, frag[2]);
@@ -80,41 +80,46 @@ struct LutDecoder {
 
 template <int E, bool SPLIT>
 __global__ void __launch_bounds__(kGemvThreads, 1)
-lut_gemv_kernel(PackSegment seg, float *__restrict__ out, const uint32_t *__restrict__ x32, const void *__restrict__ lut,
-                int r_single, int M, int K, int bs) {
+lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const uint32_t *__restrict__ x32,
+                const void *__restrict__ lut, int r_single, int M, int K, int bs) {
     using T = LutTable<E, SPLIT>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *xs = reinterpret_cast<uint32_t *>(smem + T::kBytes);
+    uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);  // compact lut copy
+    uint32_t *xs = lc + lut_compact_words(E, r_single);
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * kGemvWarps;
-    const long TT = (long)seg.strips * seg.ksuper;
-    const long lo = TT * gwarp / nwarps, hi = TT * (gwarp + 1) / nwarps;
+    unsigned lo, hi;
+    split_range(split, blockIdx.x, lo, hi);
+    const WarpRun run = warp_run(seg, lo, hi, warp_in_cta());
     uint32_t raw[kGemvDepth][TcqGeom<E>::kRawWords];
-    gemv_prefetch<E>(seg, lo, hi, raw);
-    lut_build_table<E, SPLIT>(tab, lut, r_single);
+    gemv_prefetch<E>(seg, run, raw);
+    coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
+    __syncthreads();
+    lut_build_table<E, SPLIT>(tab, lc, r_single);
     pdl_wait();
     stage_x(xs, x32, K, bs);
     __syncthreads();
     pdl_launch_dependents();
-    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & T::kLaneMask) << 2);
-    gemv_run_segment<LutDecoder<E, SPLIT>>(seg, out, M, bs, smem_u32(xs), tab_addr_lane, lo, hi, raw);
+    const uint8_t *tab_addr_lane = smem + ((lane & T::kLaneMask) << 2);
+    gemv_run_segment<LutDecoder<E, SPLIT>>(seg, out, M, bs, reinterpret_cast<const uint8_t *>(xs), tab_addr_lane, run, raw);
 }
 
 template <int E, bool SPLIT>
 __global__ void __launch_bounds__(kGemvThreads, 1)
-lut_dequant_kernel(PackSegment seg, __half *__restrict__ W, const void *__restrict__ lut, int r_single, int K) {
+lut_dequant_kernel(PackSegment seg, RunSplit split, __half *__restrict__ W, const void *__restrict__ lut, int r_single,
+                   int K) {
     using T = LutTable<E, SPLIT>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * kGemvWarps;
-    lut_build_table<E, SPLIT>(tab, lut, r_single);
+    const int gwarp = blockIdx.x * kGemvWarps + warp_in_cta();
+    uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);
+    coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
     __syncthreads();
-    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & T::kLaneMask) << 2);
-    dequant_run_segment<LutDecoder<E, SPLIT>>(seg, W, K, tab_addr_lane, gwarp, nwarps);
+    lut_build_table<E, SPLIT>(tab, lc, r_single);
+    __syncthreads();
+    const uint8_t *tab_addr_lane = smem + ((lane & T::kLaneMask) << 2);
+    dequant_run_segment<LutDecoder<E, SPLIT>>(seg, W, K, tab_addr_lane, split, gwarp);
 }
 
 template <int E, bool SPLIT>
@@ -127,8 +132,9 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    const size_t smem = (size_t)T::kBytes + (size_t)K * bs * 2;
-    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg, out, (const uint32_t *)x, lut,
+    const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2;
+    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg,
+                       make_split((long)seg.strips * seg.ksuper, sm_count()), out, (const uint32_t *)x, lut,
                        r_single, M, K, bs));
     return check_launch("lut_gemv");
 }
@@ -142,7 +148,8 @@ static int launch_lut_dequant(PackSegment seg, __half *W, const void *lut, int r
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    kern<<<sm_count(), kGemvThreads, T::kBytes, st>>>(seg, W, lut, r_single, K);
+    kern<<<sm_count(), kGemvThreads, T::kBytes + 4 * lut_compact_words(E, r_single), st>>>(
+        seg, make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), W, lut, r_single, K);
     return check_launch("lut_dequant");
 }
 
@@ -219,7 +226,8 @@ extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, con
     QP_CHECK_ARG(bs >= 1 && bs <= 8, "bs = %d: the fused GEMV handles 1..8 rows", bs);
     int rc = lut_check(codes, M, K, bits, vec_sz);
     if (rc != QP_OK) return rc;
-    const size_t avail = (size_t)kMaxSmem - (size_t)lut_table_bytes(bits, vec_sz);
+    if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
+    const size_t avail = (size_t)kMaxSmem - (size_t)lut_table_bytes(bits, vec_sz) - 16 * 1024;
     int chunk = (int)(avail / ((size_t)K * 2));
     QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
     if (chunk > bs) chunk = bs;

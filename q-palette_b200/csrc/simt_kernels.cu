@@ -23,13 +23,12 @@ struct SimtTable {
 };
 
 template <int BITS, int VEC>
-__device__ __forceinline__ void simt_build_table(uint32_t *tab, const void *__restrict__ lut) {
+__device__ __forceinline__ void simt_build_table(uint32_t *tab, const uint32_t *lc) {
     using T = SimtTable<BITS>;
     constexpr int copies = 1 << (T::kSL - 2);
     for (int i = threadIdx.x; i < (1 << BITS) * copies; i += blockDim.x) {
         const int e = i / copies;
-        tab[i] = (VEC == 2) ? reinterpret_cast<const uint32_t *>(lut)[e]
-                            : (uint32_t) reinterpret_cast<const uint16_t *>(lut)[e];
+        tab[i] = (VEC == 2) ? lc[e] : (uint32_t) reinterpret_cast<const uint16_t *>(lc)[e];
     }
 }
 
@@ -118,17 +117,20 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
     constexpr int NG = 4 * VEC;
     constexpr int kChunk = 32 * 32 * VEC;
     extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kCompactWords = (1 << BITS) * VEC / 2;
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *xs = reinterpret_cast<uint32_t *>(smem + T::kBytes);
+    uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);
+    uint32_t *xs = lc + (kCompactWords < 4 ? 4 : kCompactWords);
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * kSimtWarps + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * kSimtWarps;
 
-    simt_build_table<BITS, VEC>(tab, lut);
+    coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), kCompactWords);
+    __syncthreads();
+    simt_build_table<BITS, VEC>(tab, lc);
     if (GEMV) {
         pdl_wait();
-        const uint32_t *x32 = reinterpret_cast<const uint32_t *>(x);
-        for (int i = threadIdx.x; i < bs * K / 2; i += blockDim.x) xs[i] = x32[i];
+        coop_copy_words(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
     }
     __syncthreads();
     pdl_launch_dependents();
@@ -179,7 +181,8 @@ static int launch_simt(__half *out, const void *codes, const void *x, const void
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    const size_t smem = (size_t)SimtTable<BITS>::kBytes + (GEMV ? (size_t)K * bs * 2 : 0);
+    const size_t smem = (size_t)SimtTable<BITS>::kBytes + 4 * (size_t)(((1 << BITS) * VEC / 2) < 4 ? 4 : ((1 << BITS) * VEC / 2)) +
+                        (GEMV ? (size_t)K * bs * 2 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem, "bs*K = %d*%d does not fit the shared-memory x stage", bs, K);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kSimtThreads), smem, st, out, (const uint32_t *)codes,
                        (const __half *)x, lut, M, K, bs));

@@ -18,6 +18,21 @@
 
 namespace qp {
 
+#ifdef QP_PROFILE_PHASES
+// debug build only: per-CTA %globaltimer stamps of the GEMV phases (read back with qp_debug_phases)
+__device__ unsigned long long g_phase[256][8];
+__device__ __forceinline__ void phase_stamp(int i) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_phase[blockIdx.x][i] = t;
+    }
+}
+#define QP_PHASE(i) phase_stamp(i)
+#else
+#define QP_PHASE(i)
+#endif
+
 constexpr int kTcqThreads = kGemvThreads;
 constexpr int kTcqWarps = kGemvWarps;
 
@@ -38,29 +53,40 @@ struct TcqTable {
     static constexpr uint32_t kLaneMask = (1u << (kStrideLog2 - 2)) - 1u;
 };
 
+// lane-replicated codebook straight from global memory: every thread first issues all its tlut loads (one L2 round
+// trip), then stores.  A warp store covers 4 consecutive 128-byte slots (8 lanes x 16 bytes each).
 template <int S>
 __device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *__restrict__ tlut) {
     using T = TcqTable<S>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (T::kStrideLog2 == 7) {
-        for (int e = warp; e < T::kEntries; e += kTcqWarps) {
-            uint32_t v = __ldg(tlut + (e & ((1 << S) - 1)));
-            if (T::kFold && (e >> S)) v ^= 0x8000u;  // negate component 0 (low half)
-            tab[e * 32 + lane] = v;
-        }
-    } else {  // 16 copies per entry: one warp store covers two entries
-        for (int e2 = warp; e2 < T::kEntries / 2; e2 += kTcqWarps) {
-            const int e = e2 * 2 + (lane >> 4);
-            tab[e * 16 + (lane & 15)] = __ldg(tlut + e);
-        }
+    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+    constexpr int kRows = T::kBytes / 128;              // 128-byte rows of the table
+    constexpr int kIter = (kRows + kGemvWarps * 4 - 1) / (kGemvWarps * 4);
+    uint32_t v[kIter];
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
+        int e;
+        if (T::kStrideLog2 == 7) e = r & ((1 << S) - 1);                 // row = entry (sign variants share tlut[e])
+        else e = 2 * r + ((lane >> 2) & 1);                              // 64-byte slots: two entries per row
+        v[it] = (r < kRows) ? __ldg(tlut + e) : 0u;
+        if (T::kFold && (r >> S)) v[it] ^= 0x8000u;                       // negate component 0 (low half)
+    }
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
+        if (r < kRows) t4[r * 8 + (lane & 7)] = make_uint4(v[it], v[it], v[it], v[it]);
     }
 }
 
 template <int S>
-__device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_addr_lane, uint32_t u) {
+__device__ __forceinline__ uint32_t tcq_lookup(const uint8_t *tab_lane, uint32_t u) {
     using T = TcqTable<S>;
     const uint32_t t = tcq_hash(u);
-    uint32_t w = lds_u32(tab_addr_lane + ((t << T::kShift) & T::kMask));
+    // slot offset = hash bits [15-S, 15-S+kEntryBits) moved to [kStrideLog2, ...); tab_lane already carries the lane's
+    // 4-byte column, so the address is base + offset with no further arithmetic
+    const uint32_t off = ((T::kShift == 1) ? (t + t) : (t << T::kShift)) & T::kMask;
+    uint32_t w = *reinterpret_cast<const uint32_t *>(tab_lane + off);
     if (!T::kFold) w ^= (t & 0x8000u);
     return w;
 }
@@ -69,11 +95,9 @@ __device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_addr_lane, uint32_t 
 template <int KV, int S>
 struct TcqDecoder {
     static constexpr int kE = KV;
-    __device__ static __forceinline__ void decode(const uint32_t (&raw)[TcqGeom<KV>::kRawWords], int bitoff, int lane,
-                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
+    __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<KV>::kWords], int lane,
+                                                  const uint8_t *tab_addr_lane, uint32_t (&frag)[4][4]) {
         using G = TcqGeom<KV>;
-        uint32_t P[G::kWords];
-        tcq_align<KV>(raw, bitoff, P);
         uint32_t send[4] = {tcq_send<KV, 0>(P), tcq_send<KV, 1>(P), tcq_send<KV, 2>(P), tcq_send<KV, 3>(P)};
         uint32_t n1[4], n2[4];
 #pragma unroll
@@ -98,54 +122,66 @@ using TcqSegment = PackSegment;
 // ---- GEMV -----------------------------------------------------------------------------------------------------------
 template <int KVA, int KVB, int S>
 __global__ void __launch_bounds__(kTcqThreads, 1)
-tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, float *__restrict__ out, const uint32_t *__restrict__ x32,
-                const uint32_t *__restrict__ tlut, int M, int K, int bs) {
+tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
+                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     uint32_t *xs = reinterpret_cast<uint32_t *>(smem + TcqTable<S>::kBytes);
 
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kTcqWarps + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * kTcqWarps;
-
-    // even split of each part's super-tiles over all warps of the grid
-    const long TA = (long)segA.strips * segA.ksuper;
-    const long loA = TA * gwarp / nwarps, hiA = TA * (gwarp + 1) / nwarps;
+    const int warp = warp_in_cta();
+    QP_PHASE(0);
+    // this CTA's contiguous range of each part; its warps interleave inside it
+    unsigned loA, hiA;
+    split_range(splitA, blockIdx.x, loA, hiA);
+    const WarpRun runA = warp_run(segA, loA, hiA, warp);
     uint32_t rawA[kGemvDepth][TcqGeom<KVA>::kRawWords];
-    gemv_prefetch<KVA>(segA, loA, hiA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
-
+    gemv_prefetch<KVA>(segA, runA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
+    QP_PHASE(1);
     tcq_build_table<S>(tab, tlut);
+    QP_PHASE(2);
     pdl_wait();  // x (and out) are produced by the preceding kernel
+    QP_PHASE(3);
     stage_x(xs, x32, K, bs);
     __syncthreads();
+    QP_PHASE(4);
     pdl_launch_dependents();
 
-    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & TcqTable<S>::kLaneMask) << 2);
-    const uint32_t xs_addr = smem_u32(xs);
-    gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, loA, hiA, rawA);
-    if constexpr (KVB != 0) {
-        const long TB = (long)segB.strips * segB.ksuper;
-        const long loB = TB * gwarp / nwarps, hiB = TB * (gwarp + 1) / nwarps;
+    const uint8_t *tab_addr_lane = smem + ((lane & TcqTable<S>::kLaneMask) << 2);
+    const uint8_t *xs_addr = reinterpret_cast<const uint8_t *>(xs);
+    if constexpr (KVB == 0) {
+        gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA);
+    } else {
+        unsigned loB, hiB;
+        split_range(splitB, blockIdx.x, loB, hiB);
+        const WarpRun runB = warp_run(segB, loB, hiB, warp);
         uint32_t rawB[kGemvDepth][TcqGeom<KVB>::kRawWords];
-        gemv_prefetch<KVB>(segB, loB, hiB, rawB);
-        gemv_run_segment<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, loB, hiB, rawB);
+        // the second part's first loads are issued while the first part drains
+        gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
+                                             [&] { gemv_prefetch<KVB>(segB, runB, rawB); });
+        gemv_run_segment<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB);
     }
+#ifdef QP_PROFILE_PHASES
+    QP_PHASE(5);  // thread 0's warp done
+    __syncthreads();
+    QP_PHASE(6);  // whole CTA done
+#endif
 }
 
 // ---- dequantise -----------------------------------------------------------------------------------------------------
 template <int KVA, int KVB, int S>
 __global__ void __launch_bounds__(kTcqThreads, 1)
-tcq_dequant_kernel(TcqSegment segA, TcqSegment segB, __half *__restrict__ W, const uint32_t *__restrict__ tlut, int K) {
+tcq_dequant_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, __half *__restrict__ W,
+                   const uint32_t *__restrict__ tlut, int K) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kTcqWarps + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * kTcqWarps;
+    const int gwarp = blockIdx.x * kTcqWarps + warp_in_cta();
     tcq_build_table<S>(tab, tlut);
     __syncthreads();
-    const uint32_t tab_addr_lane = smem_u32(tab) + ((lane & TcqTable<S>::kLaneMask) << 2);
-    dequant_run_segment<TcqDecoder<KVA, S>>(segA, W, K, tab_addr_lane, gwarp, nwarps);
-    if constexpr (KVB != 0) dequant_run_segment<TcqDecoder<KVB, S>>(segB, W, K, tab_addr_lane, gwarp, nwarps);
+    const uint8_t *tab_addr_lane = smem + ((lane & TcqTable<S>::kLaneMask) << 2);
+    dequant_run_segment<TcqDecoder<KVA, S>>(segA, W, K, tab_addr_lane, splitA, gwarp);
+    if constexpr (KVB != 0) dequant_run_segment<TcqDecoder<KVB, S>>(segB, W, K, tab_addr_lane, splitB, gwarp);
 }
 
 // ---- host dispatch --------------------------------------------------------------------------------------------------
@@ -194,8 +230,10 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kTcqThreads), smem, st, L.a, L.b, out, (const uint32_t *)x,
-                       (const uint32_t *)tlut, M, K, bs));
+    const int nctas = sm_count();
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
+                       make_split((long)L.a.strips * L.a.ksuper, nctas), make_split((long)L.b.strips * L.b.ksuper, nctas),
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs));
     return check_launch("tcq_gemv");
 }
 
@@ -207,7 +245,10 @@ static int launch_dequant(const TcqLaunch &L, __half *W, const void *tlut, int K
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    kern<<<sm_count(), kTcqThreads, TcqTable<S>::kBytes, st>>>(L.a, L.b, W, (const uint32_t *)tlut, K);
+    const int nwarps = sm_count() * kTcqWarps;
+    kern<<<sm_count(), kTcqThreads, TcqTable<S>::kBytes, st>>>(
+        L.a, L.b, make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps), W,
+        (const uint32_t *)tlut, K);
     return check_launch("tcq_dequant");
 }
 
@@ -311,7 +352,7 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     if (rc != QP_OK) return rc;
     if ((rc = check_align(codes1, 16, "codes1")) != QP_OK) return rc;
     if (codes2 && (rc = check_align(codes2, 16, "codes2")) != QP_OK) return rc;
-    if ((rc = check_align(x_f16, 4, "x")) != QP_OK) return rc;
+    if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
     if ((rc = check_align(tlut_f16, 4, "tlut")) != QP_OK) return rc;
     // x lives in shared memory next to the 128 KiB codebook: process the batch in chunks that fit
     const size_t avail = (size_t)kMaxSmem - 128 * 1024;
@@ -351,3 +392,10 @@ extern "C" int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *cod
     QP_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)bs * M * 4, cudaMemcpyDeviceToHost, st));
     return QP_OK;
 }
+
+#ifdef QP_PROFILE_PHASES
+extern "C" int qp_debug_phases(unsigned long long *host_out /* [256][8] */) {
+    QP_CUDA(cudaMemcpyFromSymbol(host_out, qp::g_phase, sizeof(unsigned long long) * 256 * 8));
+    return QP_OK;
+}
+#endif

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpalette.so")
+LIB_PATH = os.path.join(_HERE, f"libqpalette{os.environ.get('QP_LIB_SUFFIX', '')}.so")
 
 QP_OK = 0
 SPLIT_NONE, SPLIT_IN, SPLIT_OUT = 0, 1, 2
