@@ -74,8 +74,8 @@ int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, i
  * vq_pack_gemm.vq_pack_gemm_* / vq_pack_dequant_* (kernels/vq-cuda-kernels/src/gemm_routines.cu:1913-2120).
  * Accumulates in fp32 (the reference accumulates in fp16).
  * ------------------------------------------------------------------------------------------------------------- */
-int qp_simt_gemv(void *out_f16, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
-                 int bits, int vec_sz, void *stream);
+int qp_simt_gemv(void *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
+                 int bits, int vec_sz, int out_is_f32 /* 0: fp16 (bs,M) like the reference op; 1: fp32 */, void *stream);
 int qp_simt_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,
                     void *stream);
 /* GPU version of lib/quantizer/quant_op.py:246-257 convert_tensor_core_to_simt (format conversion at load time) */
@@ -96,6 +96,33 @@ int qp_hadamard(void *y, const void *x, const void *su_f16, int rows, int n, flo
  * The `.to(fp16) * Wscale * scale` (+ split + SiLU*mul) glue of lib/linear/incoherent_linear.py:83-108,326-338. */
 int qp_scale_epilogue(void *out_f16, const float *acc, const void *wscale_f16, int bs, int M, float scale,
                       int epilogue, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Decode-step glue (bs = 1).  The reference runs these as torch eager ops fused by torch.compile/Inductor
+ * (eval/measure_latency.py:223-225); north_star rules Triton out, so they are kernels here.  All are latency-bound
+ * single-/few-CTA kernels that read their scalars (token, position) from DEVICE memory so that one decode step can be
+ * captured once as a CUDA graph and replayed per token.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* [h += fp16(acc)*wscale*acc_scale (written back if h_writeback)] -> [RMSNorm(norm_w, eps)] -> [*su] -> [Hadamard] ->
+ * x_out = fp16(. * had_scale).  acc/wscale, norm_w, su may be NULL.  Also zeroes zero_count floats at zero_ptr (the next
+ * GEMV's accumulators).  lib/linear/incoherent_linear.py:76-108,324-338 + LlamaDecoderLayer residual/RMSNorm. */
+int qp_fused_norm_had(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
+                      float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
+                      int do_had, float *zero_ptr, int zero_count, void *stream);
+/* acc = [up | gate] (2*I fp32): x_out = fp16(Hadamard(silu(gate)*up * su) * had_scale)   (IncoherentMLP.compute_ug tail
+ * + compute_dp head, lib/linear/incoherent_linear.py:324-338) */
+int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *wscale_f16, float acc_scale, const void *su_f16,
+                    int I, float had_scale, float *zero_ptr, int zero_count, void *stream);
+/* acc_qkv = [q | k | v] fp32 GEMV sums: Wscale epilogue, RoPE, KV-cache append at *pos_ptr, causal attention of the new
+ * token over the cache; one CTA per query head (IncoherentSdpaAttention.forward, lib/linear/incoherent_linear.py:110-203) */
+int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,
+                      const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H, int Hkv,
+                      int D, int max_seq, float *zero_ptr, int zero_count, void *stream);
+/* fp16 GEMV for the unquantized lm_head: out (rows) fp32 = W (rows, K) @ x (K) */
+int qp_gemv_f16(float *out, const void *W_f16, const void *x_f16, int rows, int K, void *stream);
+int qp_argmax(int *token_out, const float *logits, int n, void *scratch, void *stream);
+int qp_embed(void *h_f16, const void *table_f16, const int *token, int n, void *stream);
+int qp_step_advance(int *pos, int *history, const int *token, int max_hist, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * host-buffer variant used for end-to-end timing: x_host (bs,K) fp16 pinned/pageable host memory, out_host (bs,M)

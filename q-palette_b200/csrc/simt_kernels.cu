@@ -112,7 +112,7 @@ __device__ __forceinline__ void simt_groups_store(const uint32_t (&w)[BITS], uin
 template <int BITS, int VEC, bool GEMV>
 __global__ void __launch_bounds__(kSimtThreads, 1)
 simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const __half *__restrict__ x,
-            const void *__restrict__ lut, int M, int K, int bs) {
+            const void *__restrict__ lut, int M, int K, int bs, int out_f32) {
     using T = SimtTable<BITS>;
     constexpr int NG = 4 * VEC;
     constexpr int kChunk = 32 * 32 * VEC;
@@ -165,7 +165,10 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
                     float v = acc[n];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) out[(size_t)n * M + row] = __float2half(v);
+                    if (lane == 0) {
+                        if (out_f32) reinterpret_cast<float *>(out)[(size_t)n * M + row] = v;
+                        else out[(size_t)n * M + row] = __float2half(v);
+                    }
                 }
             }
         }
@@ -174,7 +177,7 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
 
 template <int BITS, int VEC, bool GEMV>
 static int launch_simt(__half *out, const void *codes, const void *x, const void *lut, int M, int K, int bs,
-                       cudaStream_t st) {
+                       int out_f32, cudaStream_t st) {
     auto kern = simt_kernel<BITS, VEC, GEMV>;
     static bool configured = false;
     if (!configured) {
@@ -185,15 +188,15 @@ static int launch_simt(__half *out, const void *codes, const void *x, const void
                         (GEMV ? (size_t)K * bs * 2 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem, "bs*K = %d*%d does not fit the shared-memory x stage", bs, K);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kSimtThreads), smem, st, out, (const uint32_t *)codes,
-                       (const __half *)x, lut, M, K, bs));
+                       (const __half *)x, lut, M, K, bs, out_f32));
     return check_launch(GEMV ? "simt_gemv" : "simt_dequant");
 }
 
 template <bool GEMV>
 static int dispatch_simt(int bits, int vec_sz, __half *out, const void *codes, const void *x, const void *lut, int M,
-                         int K, int bs, cudaStream_t st) {
+                         int K, int bs, int out_f32, cudaStream_t st) {
 #define QP_C(B, V) \
-    if (bits == B && vec_sz == V) return launch_simt<B, V, GEMV>(out, codes, x, lut, M, K, bs, st);
+    if (bits == B && vec_sz == V) return launch_simt<B, V, GEMV>(out, codes, x, lut, M, K, bs, out_f32, st);
     QP_C(2, 1) QP_C(3, 1) QP_C(4, 1) QP_C(5, 1) QP_C(6, 1) QP_C(7, 1) QP_C(8, 1)
     QP_C(2, 2) QP_C(3, 2) QP_C(4, 2) QP_C(5, 2) QP_C(6, 2) QP_C(7, 2) QP_C(8, 2) QP_C(9, 2) QP_C(10, 2) QP_C(11, 2)
     QP_C(12, 2)
@@ -261,14 +264,16 @@ static int simt_check(const void *codes, int M, int K, int bits, int vec_sz) {
     return check_align(codes, 4, "codes");
 }
 
-extern "C" int qp_simt_gemv(void *out_f16, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
-                            int bits, int vec_sz, void *stream) {
+extern "C" int qp_simt_gemv(void *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
+                            int bits, int vec_sz, int out_is_f32, void *stream) {
+    void *out_f16 = out;
     QP_CHECK_ARG(out_f16 && x_f16 && lut_f16, "NULL pointer argument");
     QP_CHECK_ARG(bs >= 1 && bs <= 8, "bs = %d: the fused GEMV handles 1..8 rows", bs);
     int rc = simt_check(codes, M, K, bits, vec_sz);
     if (rc != QP_OK) return rc;
     if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
-    return dispatch_simt<true>(bits, vec_sz, (__half *)out_f16, codes, x_f16, lut_f16, M, K, bs, (cudaStream_t)stream);
+    return dispatch_simt<true>(bits, vec_sz, (__half *)out_f16, codes, x_f16, lut_f16, M, K, bs, out_is_f32,
+                               (cudaStream_t)stream);
 }
 
 extern "C" int qp_simt_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,
@@ -277,7 +282,7 @@ extern "C" int qp_simt_dequant(void *W_f16, const void *codes, const void *lut_f
     int rc = simt_check(codes, M, K, bits, vec_sz);
     if (rc != QP_OK) return rc;
     if ((rc = check_align(W_f16, 16, "W")) != QP_OK) return rc;
-    return dispatch_simt<false>(bits, vec_sz, (__half *)W_f16, codes, nullptr, lut_f16, M, K, 1, (cudaStream_t)stream);
+    return dispatch_simt<false>(bits, vec_sz, (__half *)W_f16, codes, nullptr, lut_f16, M, K, 1, 0, (cudaStream_t)stream);
 }
 
 extern "C" int qp_convert_tc_to_simt(void *simt_codes, const void *tc_codes, int M, int K, int bits, int vec_sz,

@@ -25,11 +25,18 @@ SIGNATURES = {
     "qp_tcq_dequant": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "qp_lut_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "qp_simt_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "qp_simt_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "qp_simt_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_convert_tc_to_simt": [_vp, _vp, _i, _i, _i, _i, _vp],
     "qp_hadamard": [_vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
+    "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
+    "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "qp_gemv_f16": [_vp, _vp, _vp, _i, _i, _vp],
+    "qp_argmax": [_vp, _vp, _i, _vp, _vp],
+    "qp_embed": [_vp, _vp, _vp, _i, _vp],
+    "qp_step_advance": [_vp, _vp, _vp, _i, _vp],
     "qp_tcq_gemv_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64}

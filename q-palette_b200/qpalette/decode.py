@@ -1,0 +1,336 @@
+"""bs=1 decode loop for Llama-shaped models built from Q-Palette quantized layers (the path eval/measure_latency.py times).
+
+The reference wraps a HF Llama with `torch.compile(mode="max-autotune", fullgraph=True)` + CUDA graphs
+(eval/measure_latency.py:188-273).  Here the decode step is an explicit, flat list of libqpalette kernel launches
+(4 quantized GEMVs + 5 fused glue kernels per layer, see csrc/decode_kernels.cu) captured ONCE into a CUDA graph;
+token and position live in device memory, so the same graph is replayed for every token.
+
+Layers come from a `qdict` ("{layer}_{self_attn.q_proj|...|mlp.down_proj}" -> quantizer_str or (quantizer_str, simt_flag))
+and a `merge_info` (per-layer list from {merge_qkv, merge_qk, merge_kv, merge_qv, merge_ug}), exactly the reference's
+formats (eval/measure_latency_merge_simt.py:60-71, solve_lat_const.py:152-162), with the reference's `--dummy` random
+initialisation (lib/utils/mem_op.py:198-269) since no checkpoints are reachable offline.
+
+Row sharding (tensor parallel over output rows): with world_size > 1 every rank keeps the rows
+[rank, rank+1) * M/world of each projection (a zero-copy slice of the strip-major packed buffers) and the partial outputs
+are all-gathered with NCCL at the four layer boundaries.
+"""
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _cabi
+from ._cabi import FLAG_ACCUMULATE, SPLIT_IN, SPLIT_NONE, check, lib
+from .linear.incoherent_linear import rope_inv_freq
+from .utils.mem_op import get_dummy_quant_results, get_quant_info
+
+
+@dataclass
+class LlamaShape:
+    hidden_size: int = 4096
+    intermediate_size: int = 14336
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    num_key_value_heads: int = 8
+    vocab_size: int = 128256
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    rope_scaling: dict = field(default_factory=lambda: dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0,
+                                                            high_freq_factor=4.0, original_max_position_embeddings=8192))
+    hidden_act: str = "silu"
+    attention_dropout: float = 0.0
+    max_position_embeddings: int = 131072
+    _name_or_path: str = "meta-llama/Llama-3.1-8B"
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_attention_heads
+
+
+LLAMA31_8B = LlamaShape()
+LLAMA31_70B = LlamaShape(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64,
+                         num_key_value_heads=8, _name_or_path="meta-llama/Llama-3.1-70B")
+
+
+def uniform_qdict(shape, quantizer_str, simt="0"):
+    keys = ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.up_proj",
+            "mlp.gate_proj", "mlp.down_proj"]
+    return {f"{i}_{k}": (quantizer_str, simt) for i in range(shape.num_hidden_layers) for k in keys}
+
+
+class _Proj:
+    """one quantized projection (possibly a merged one): packed buffers + what the C ABI needs to run its GEMV."""
+
+    def __init__(self, quantizer_str, simt, in_features, out_features, device, gen, rank=0, world=1, group_sizes=None):
+        self.qs, self.K = quantizer_str, in_features
+        qi = get_quant_info(quantizer_str)
+        self.kind = qi["quantizer"]
+        info = get_dummy_quant_results(None, None, quantizer_str, device=device, generator=gen, in_features=in_features,
+                                       out_features=out_features)["linear_info"]
+        self.M_full = out_features
+        # row shard: keep rows [rank, rank+1) * M/world of every merged member (zero-copy slices: strip-major layout)
+        sizes = group_sizes or [out_features]
+        rows = []
+        base = 0
+        for s in sizes:
+            assert s % (32 * world) == 0, f"rows {s} not divisible into {world} shards of 32-row strips"
+            per = s // world
+            rows.append((base + rank * per, per))
+            base += s
+        self.M = sum(p for _, p in rows)
+
+        def shard(t):
+            """rows are strip-major in every packed layout: a block of 32*k rows is one contiguous flat range"""
+            flat = t.reshape(-1)
+            if world == 1 and len(rows) == 1:
+                return flat
+            per_row = flat.numel() // out_features
+            return torch.cat([flat[r0 * per_row:(r0 + n) * per_row] for r0, n in rows]).contiguous()
+
+        self.bufs = []
+        if self.kind == "tcq_ldlq":
+            self.S, self.KV1, self.KV2, self.split, self.part1 = qi["tlut_bits"], qi["KV"], 0, SPLIT_NONE, 0
+            self.codes1, self.codes2 = shard(info["trellis"]), None
+            self.lut = info["tlut"]
+            self.bits_per_weight = qi["KV"] / 2
+        elif self.kind == "combt_ldlq":
+            self.S, (self.KV1, self.KV2), self.split, self.part1 = qi["tlut_bits"], qi["KV"], SPLIT_IN, in_features // 2
+            self.codes1, self.codes2 = shard(info["trellis1"]), shard(info["trellis2"])
+            self.lut = info["tlut"]
+            self.bits_per_weight = (qi["KV"][0] + qi["KV"][1]) / 4
+        elif self.kind in ("vq_ldlq", "vq"):
+            self.bits, self.vec = qi["lut_bits"], qi["vec_sz"]
+            self.lut = info["lut"]
+            self.simt = bool(int(simt)) and self.vec <= 2
+            qw = shard(info["qweight"])
+            if self.simt:
+                out = torch.empty_like(qw)
+                check(lib().qp_convert_tc_to_simt(out.data_ptr(), qw.data_ptr(), self.M, in_features, self.bits, self.vec,
+                                                  torch.cuda.current_stream().cuda_stream))
+                qw = out
+            self.codes1, self.codes2 = qw, None
+            self.bits_per_weight = self.bits / self.vec
+        else:
+            raise ValueError(f"unsupported quantizer {quantizer_str}")
+        self.weight_bytes = self.codes1.numel() * self.codes1.element_size() + \
+            (self.codes2.numel() * self.codes2.element_size() if self.codes2 is not None else 0)
+
+    def launch(self, out_ptr, x_ptr, stream):
+        L = lib()
+        if self.kind in ("tcq_ldlq", "combt_ldlq"):
+            check(L.qp_tcq_gemv(out_ptr, self.codes1.data_ptr(), self.codes2.data_ptr() if self.codes2 is not None else None,
+                                x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.S, self.KV1, self.KV2, self.split,
+                                self.part1, FLAG_ACCUMULATE, stream))
+        elif self.simt:
+            check(L.qp_simt_gemv(out_ptr, self.codes1.data_ptr(), x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.bits,
+                                 self.vec, 1, stream))
+        else:
+            check(L.qp_lut_gemv(out_ptr, self.codes1.data_ptr(), x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.bits,
+                                self.vec, FLAG_ACCUMULATE, stream))
+
+
+class DecodeRunner:
+    def __init__(self, shape=LLAMA31_8B, qdict=None, merge_info=None, max_seq=512, device="cuda", seed=0, rank=0,
+                 world=1, process_group=None, num_layers=None, random_scales=True):
+        self.shape, self.dev, self.rank, self.world, self.pg = shape, torch.device(device), rank, world, process_group
+        self.L = num_layers or shape.num_hidden_layers
+        self.max_seq = max_seq
+        qdict = qdict or uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9")
+        merge_info = merge_info or [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(seed)
+        H, kvd, I, V = shape.hidden_size, shape.num_key_value_heads * shape.head_dim, shape.intermediate_size, shape.vocab_size
+        self.H, self.kvd, self.I = H, kvd, I
+        assert shape.num_attention_heads % world == 0 and shape.num_key_value_heads % world == 0 or world == 1
+        f16 = dict(dtype=torch.float16, device=self.dev)
+
+        def rnd(*s, scale=1.0):
+            return (torch.randn(*s, generator=g, dtype=torch.float32, device=self.dev) * scale).to(torch.float16)
+
+        def signs(n):
+            return ((torch.randn(n, generator=g, device=self.dev) > 0).float() * 2 - 1).to(torch.float16)
+
+        def wscale(n):
+            # per-row scale so that quantized weights (unit variance codebooks) act like 1/sqrt(K)-scaled matrices
+            if not random_scales:
+                return torch.ones(n, **f16)
+            return (torch.rand(n, generator=g, device=self.dev) * 0.5 + 0.75).to(torch.float16)
+
+        self.embed = rnd(V, H, scale=1.0)
+        self.lm_head = rnd(V, H, scale=H ** -0.5)  # fp16, NOT quantized (eval/measure_latency.py keeps lm_head in fp16)
+        self.final_norm = torch.ones(H, **f16)
+        self.inv_freq = rope_inv_freq(shape, self.dev)
+        self.layers = []
+        self.weight_bytes = 0
+
+        def entry(i, key):
+            v = qdict[f"{i}_{key}"]
+            return (v, "0") if isinstance(v, str) else (v[0], v[1])
+
+        for i in range(self.L):
+            merges = merge_info[i] if merge_info is not None else []
+            ly = {}
+            q, k, v, o = (entry(i, f"self_attn.{n}_proj") for n in "qkvo")
+            up, gate, down = (entry(i, f"mlp.{n}_proj") for n in ("up", "gate", "down"))
+            mk = lambda e, kin, m, sizes=None: _Proj(e[0], e[1], kin, m, self.dev, g, rank, world, sizes)
+            # attention projections: list of (proj, offset into the [q|k|v] accumulator of THIS rank)
+            Hq, Hk = H // world, kvd // world
+            if "merge_qkv" in merges:
+                ly["qkv"] = [(mk(q, H, H + 2 * kvd, [H, kvd, kvd]), 0)]
+            elif "merge_qk" in merges:
+                ly["qkv"] = [(mk(q, H, H + kvd, [H, kvd]), 0), (mk(v, H, kvd), Hq + Hk)]
+            elif "merge_kv" in merges:
+                ly["qkv"] = [(mk(q, H, H), 0), (mk(k, H, 2 * kvd, [kvd, kvd]), Hq)]
+            elif "merge_qv" in merges:
+                raise NotImplementedError("merge_qv is not used by the shipped MSQ solutions")
+            else:
+                ly["qkv"] = [(mk(q, H, H), 0), (mk(k, H, kvd), Hq), (mk(v, H, kvd), Hq + Hk)]
+            ly["o"] = mk(o, H, H)
+            Il = I // world
+            if "merge_ug" in merges:
+                ly["ug"] = [(mk(up, H, 2 * I, [I, I]), 0)]
+            else:
+                ly["ug"] = [(mk(up, H, I), 0), (mk(gate, H, I), Il)]
+            ly["down"] = mk(down, I, H)
+            ly["norm1"], ly["norm2"] = torch.ones(H, **f16), torch.ones(H, **f16)
+            ly["SU_qkv"], ly["SU_o"], ly["SU_ug"], ly["SU_dp"] = signs(H), signs(H), signs(H), signs(I)
+            # Wscale ~ 1/sqrt(K)/s keeps activations O(1) through random-init layers (Wscale is per output row)
+            ly["W_qkv"] = wscale(Hq + 2 * Hk) * (H ** -0.5)
+            ly["W_o"] = wscale(H // world) * (H ** -0.5)
+            ly["W_ug"] = wscale(2 * Il) * (H ** -0.5)
+            ly["W_dp"] = wscale(H // world) * (I ** -0.5)
+            for name in ("W_qkv", "W_o", "W_ug", "W_dp"):
+                ly[name] = ly[name].to(torch.float16)
+            ly["kc"] = torch.zeros((max_seq, shape.num_key_value_heads // world, shape.head_dim), **f16)
+            ly["vc"] = torch.zeros_like(ly["kc"])
+            for p in [pp for pp, _ in ly["qkv"]] + [ly["o"]] + [pp for pp, _ in ly["ug"]] + [ly["down"]]:
+                self.weight_bytes += p.weight_bytes
+            self.layers.append(ly)
+
+        z32 = dict(dtype=torch.float32, device=self.dev)
+        Hq, Hk, Il = H // world, kvd // world, I // world
+        self.h = torch.zeros(H, **f16)
+        self.x_h = torch.zeros(H, **f16)
+        self.x_i = torch.zeros(I, **f16)
+        self.attn = torch.zeros(H, **f16)       # full attention output (all-gathered when sharded)
+        self.attn_loc = torch.zeros(Hq, **f16)
+        self.acc_qkv = torch.zeros(Hq + 2 * Hk, **z32)
+        self.acc_o = torch.zeros(H, **z32)       # full width; each rank fills its slice, then all-gather
+        self.acc_ug = torch.zeros(2 * Il, **z32)
+        self.acc_dn = torch.zeros(H, **z32)
+        self.act_loc = torch.zeros(Il, **f16)    # sharded silu(gate)*up
+        self.act = torch.zeros(I, **f16)
+        self.xf = torch.zeros(H, **f16)
+        self.logits = torch.zeros(V, **z32)
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.history = torch.zeros(max_seq, dtype=torch.int32, device=self.dev)
+        self.scratch = torch.zeros(4096, dtype=torch.uint8, device=self.dev)
+        self.graph = None
+        self.lm_head_bytes = self.lm_head.numel() * 2
+        self.launches_per_step = 0
+        self._prepare_full_scales()
+
+    # -----------------------------------------------------------------------------------------------------------------
+    def _step(self):
+        """enqueue one decode step on the current stream (eager; also what gets captured into the graph)."""
+        L, st = lib(), torch.cuda.current_stream().cuda_stream
+        sh, H, I = self.shape, self.H, self.I
+        world, rank = self.world, self.rank
+        n0 = _cabi.launch_count()
+        p = lambda t: t.data_ptr()
+        s_h, s_i, S = 1.0 / (math.sqrt(H) * 64.0), 1.0 / (math.sqrt(I) * 64.0), 64.0
+        Hq, Hk, Il, Ho = H // world, self.kvd // world, I // world, H // world
+        check(L.qp_embed(p(self.h), p(self.embed), p(self.token), H, st))
+        prev = None
+        for ly in self.layers:
+            # residual from the previous layer's down_proj, input_layernorm, SU, Hadamard -> x_h ; zero acc_qkv
+            if prev is None:
+                check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 0, None, None, 0.0, p(ly["norm1"]), sh.rms_norm_eps,
+                                          p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv), self.acc_qkv.numel(), st))
+            else:
+                check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(ly["norm1"]),
+                                          sh.rms_norm_eps, p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv),
+                                          self.acc_qkv.numel(), st))
+            for proj, off in ly["qkv"]:
+                proj.launch(p(self.acc_qkv) + 4 * off, p(self.x_h), st)
+            attn_dst = self.attn if world == 1 else self.attn_loc
+            check(L.qp_rope_attention(p(attn_dst), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
+                                      p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
+                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, None, 0, st))
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(self.attn, self.attn_loc, group=self.pg)
+            check(L.qp_fused_norm_had(p(self.x_h), p(self.attn), 0, None, None, 0.0, None, 0.0, p(ly["SU_o"]), H, s_h, 1,
+                                      p(self.acc_o), self.acc_o.numel(), st))
+            ly["o"].launch(p(self.acc_o) + 4 * rank * Ho, p(self.x_h), st)
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(self.acc_o, self.acc_o[rank * Ho:(rank + 1) * Ho], group=self.pg)
+            check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 1, p(self.acc_o), p(ly["W_o_full"]), S, p(ly["norm2"]),
+                                      sh.rms_norm_eps, p(ly["SU_ug"]), H, s_h, 1, p(self.acc_ug), self.acc_ug.numel(), st))
+            for proj, off in ly["ug"]:
+                proj.launch(p(self.acc_ug) + 4 * off, p(self.x_h), st)
+            if world == 1:
+                check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i,
+                                        p(self.acc_dn), self.acc_dn.numel(), st))
+            else:
+                check(L.qp_scale_epilogue(p(self.act_loc), p(self.acc_ug), p(ly["W_ug"]), 1, 2 * Il, S, _cabi.EPI_SILU_MUL, st))
+                torch.distributed.all_gather_into_tensor(self.act, self.act_loc, group=self.pg)
+                check(L.qp_fused_norm_had(p(self.x_i), p(self.act), 0, None, None, 0.0, None, 0.0, p(ly["SU_dp"]), I, s_i, 1,
+                                          p(self.acc_dn), self.acc_dn.numel(), st))
+            ly["down"].launch(p(self.acc_dn) + 4 * rank * Ho, p(self.x_i), st)
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(self.acc_dn, self.acc_dn[rank * Ho:(rank + 1) * Ho], group=self.pg)
+            prev = ly
+        check(L.qp_fused_norm_had(p(self.xf), p(self.h), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
+                                  sh.rms_norm_eps, None, H, 1.0, 0, None, 0, st))
+        check(L.qp_gemv_f16(p(self.logits), p(self.lm_head), p(self.xf), sh.vocab_size, H, st))
+        check(L.qp_argmax(p(self.token), p(self.logits), sh.vocab_size, p(self.scratch), st))
+        check(L.qp_step_advance(p(self.pos), p(self.history), p(self.token), self.max_seq, st))
+        self.launches_per_step = _cabi.launch_count() - n0
+
+    def _prepare_full_scales(self):
+        """Wscale vectors of o/down as full-width tensors (every rank needs all rows after the all-gather)."""
+        for ly in self.layers:
+            for name in ("W_o", "W_dp"):
+                if self.world == 1:
+                    ly[name + "_full"] = ly[name]
+                else:
+                    full = torch.empty(self.H, dtype=torch.float16, device=self.dev)
+                    torch.distributed.all_gather_into_tensor(full, ly[name], group=self.pg)
+                    ly[name + "_full"] = full
+
+    def reset(self, token=1):
+        self.token.fill_(token)
+        self.pos.zero_()
+
+    def capture(self):
+        self.reset()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        self.reset()
+        return self
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+    def generate(self, n_tokens, token=1):
+        """greedy decode n_tokens from `token`; returns the generated ids (host list)."""
+        self.reset(token)
+        for _ in range(n_tokens):
+            self.step()
+        torch.cuda.synchronize()
+        return self.history[:n_tokens].tolist()
+
+    def bytes_per_token(self):
+        return self.weight_bytes + self.lm_head_bytes

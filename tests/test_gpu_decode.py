@@ -1,0 +1,224 @@
+"""GPU tests of the layer wrappers (reference module API) and of the fused decode step against a float64
+restatement built from the oracle's decoded weights."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def decode_info(info):
+    """oracle-decoded fp16 weight (M, K) of a linear_info dict"""
+    li = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in info.items()}
+    M, K = li["out_features"], li["in_features"]
+    if "trellis" in li:
+        return O.tcq_decode(li["trellis"], li["tlut"], M, K, li["KV"], li["tlut_bits"])
+    if "trellis1" in li and "in_part" in li:
+        return O.tcq_decode_combt(li["trellis1"], li["trellis2"], li["tlut"], M, K, li["KV"][0], li["KV"][1], li["tlut_bits"])
+    if "trellis1" in li:
+        return O.tcq_decode_comb(li["trellis1"], li["trellis2"], li["tlut"], M, K, li["KV"][0], li["KV"][1], li["tlut_bits"])
+    return O.lut_tc_decode(li["qweight"], li["lut"], M, K, li["lut_bits"], li["vec_sz"])
+
+
+@pytest.mark.parametrize("qs,simt", [("tcq_6_none_0.9", False), ("tcomb_6_7_0.5_none_0.9", False),
+                                     ("ldlq_2_8_none_1.0", False), ("ldlq_1_4_none_1.0", False),
+                                     ("ldlq_2_6_none_1.0", True), ("ldlq_1_6_none_1.0", True),
+                                     ("comb_7_8_0.5_none_0.9", False)])
+@pytest.mark.parametrize("bs", [1, 4, 12])
+def test_linear_modules_and_incoherent_linear(qs, simt, bs):
+    from qpalette.linear import IncoherentLinear, make_linear
+    from qpalette.utils import get_dummy_quant_results
+    torch.manual_seed(0)
+    K, M = 1024, 512
+    info = get_dummy_quant_results(None, None, qs, in_features=K, out_features=M)
+    W = decode_info(info["linear_info"])
+    lin = make_linear(info, use_simt=simt)
+    x = torch.randn(bs, K, device="cuda").half()
+    y = lin(x).float().cpu().numpy()
+    ref = O.gemv_ref(W, x.cpu().numpy())
+    assert y.shape == (bs, M)
+    assert rel_l2(y, ref) <= 2e-3  # fp16 output rounding of the module API on top of the 1e-3 kernel budget
+    li = lin._info()  # `_info()` keeps the reference schema
+    assert li["in_features"] == K and li["out_features"] == M and li["bias"] is None
+    # left-only incoherent layer (as shipped: rot_info = skip_r)
+    info.update(SU=((torch.randn(K) > 0).float() * 2 - 1).half(), SV=torch.ones(M).half(),
+                Wscale=(torch.rand(M) * 0.02 + 0.01).half(), hadU=K, hadV=M, rot_info="skip_r", scale=32.0)
+    info["quant_info"]["rot_info"] = "skip_r"
+    layer = IncoherentLinear.gen_layer_from_info(info, merge_layers=True, use_simt=simt)
+    if bs <= 8:
+        out = layer(x).float().cpu().numpy()
+        ref2 = O.incoherent_linear_ref(x.cpu().numpy(), W, info["SU"].numpy(), info["Wscale"].numpy(), 32.0)
+        assert rel_l2(out, ref2) <= 3e-3
+
+
+def test_merge_infos_equals_stacking():
+    from qpalette.linear import CombtLinearTCQ, QTIPLinearTCQ, VQLinearPackTensorCore
+    from qpalette.utils import get_dummy_quant_results
+    torch.manual_seed(1)
+    K = 512
+    for qs, cls in (("tcq_5_none_0.9", QTIPLinearTCQ), ("tcomb_7_8_0.5_none_0.9", CombtLinearTCQ),
+                    ("ldlq_2_9_none_1.0", VQLinearPackTensorCore)):
+        a = get_dummy_quant_results(None, None, qs, in_features=K, out_features=256)["linear_info"]
+        b = get_dummy_quant_results(None, None, qs, in_features=K, out_features=128)["linear_info"]
+        for key in ("tlut", "lut"):
+            if key in b:
+                b[key] = a[key]
+        merged = cls.gen_layer_from_info(cls.merge_infos(a, b))
+        la, lb = cls.gen_layer_from_info(a), cls.gen_layer_from_info(b)
+        x = torch.randn(2, K, device="cuda").half()
+        # same rows, different split-K partition/atomic order -> equal up to fp32 summation order
+        assert torch.allclose(merged(x).float(), torch.cat([la(x), lb(x)], dim=-1).float(), rtol=2e-3, atol=2e-2)
+
+
+def test_mlp_and_attention_modules():
+    """IncoherentMLP / IncoherentSdpaAttention (reference module API) against the float64 layer math."""
+    from qpalette.decode import LlamaShape
+    from qpalette.linear import IncoherentMLP, IncoherentSdpaAttention, StaticKVCache
+    from qpalette.utils import get_dummy_quant_results
+    torch.manual_seed(2)
+    cfg = LlamaShape(hidden_size=512, intermediate_size=28 * 32, num_hidden_layers=1, num_attention_heads=8,
+                     num_key_value_heads=2, vocab_size=64)
+    H, I, kvd = 512, 896, 128
+    mk = lambda qs, k, m: get_dummy_quant_results(None, None, qs, in_features=k, out_features=m)
+
+    def dress(info, k, m):
+        info.update(SU=((torch.randn(k) > 0).float() * 2 - 1).half(), Wscale=(torch.rand(m) * 0.02 + 0.02).half())
+        return info
+
+    up, gate, down = dress(mk("tcq_6_none_0.9", H, I), H, I), dress(mk("tcq_6_none_0.9", H, I), H, I), \
+        dress(mk("tcomb_6_7_0.5_none_0.9", I, H), I, H)
+    gate["linear_info"]["tlut"] = up["linear_info"]["tlut"]
+    x = torch.randn(1, 1, H, device="cuda").half()
+    Wu, Wg, Wd = decode_info(up["linear_info"]), decode_info(gate["linear_info"]), decode_info(down["linear_info"])
+    f = lambda t: t.float().cpu().numpy().astype(np.float64)
+    xs = f(x).reshape(-1)
+    z = O.hadamard_ref(xs * f(up["SU"])) / 64
+    u = (Wu.astype(np.float64) @ z) * f(up["Wscale"]) * 64
+    g = (Wg.astype(np.float64) @ z) * f(gate["Wscale"]) * 64
+    act = g / (1 + np.exp(-g)) * u
+    z2 = O.hadamard_ref(act * f(down["SU"])) / 64
+    ref = (Wd.astype(np.float64) @ z2) * f(down["Wscale"]) * 64
+    for merge in (False, True):
+        mlp = IncoherentMLP.gen_layer_from_info(cfg, up, gate, down, merge_ug=merge)
+        out = f(mlp(x)).reshape(-1)
+        assert rel_l2(out, ref) <= 1e-2, merge
+    # attention: merged qkv vs separate projections give the same result; cache grows
+    q, k, v, o = dress(mk("tcq_8_none_0.9", H, H), H, H), dress(mk("tcq_8_none_0.9", H, kvd), H, kvd), \
+        dress(mk("tcq_8_none_0.9", H, kvd), H, kvd), dress(mk("tcq_8_none_0.9", H, H), H, H)
+    for i in (k, v):
+        i["linear_info"]["tlut"] = q["linear_info"]["tlut"]
+    outs = []
+    for merge in (dict(), dict(merge_qkv=True), dict(merge_kv=True)):
+        attn = IncoherentSdpaAttention.gen_layer_from_info(cfg, 0, q, k, v, o, **merge)
+        cache = StaticKVCache(1, 8, 2, 64)
+        ys = []
+        for t in range(3):
+            xt = torch.full((1, 1, H), 0.1 * (t + 1), device="cuda").half() + x
+            y, _, _ = attn(xt, past_key_value=cache, cache_position=torch.tensor([t], device="cuda"))
+            ys.append(y)
+        outs.append(torch.cat(ys, 1))
+    assert torch.allclose(outs[0].float(), outs[1].float(), rtol=2e-2, atol=2e-3)
+    assert torch.allclose(outs[0].float(), outs[2].float(), rtol=2e-2, atol=2e-3)
+
+
+def _ref_layer_step(r, x_in_h, pos, caches):
+    """float64 restatement of one decode step of DecodeRunner (decoded weights from the oracle)."""
+    sh = r.shape
+    H, I = r.H, r.I
+    h = x_in_h.astype(np.float64)
+    D, nh, nkv = sh.head_dim, sh.num_attention_heads, sh.num_key_value_heads
+
+    def rms(v, w):
+        return v / np.sqrt((v * v).mean() + sh.rms_norm_eps) * w
+
+    t = lambda a: a.cpu().numpy()
+    f = lambda a: a.float().cpu().numpy().astype(np.float64)
+
+    def proj_W(p):
+        if p.kind == "tcq_ldlq":
+            return O.tcq_decode(t(p.codes1), t(p.lut), p.M, p.K, p.KV1, p.S)
+        if p.kind == "combt_ldlq":
+            return O.tcq_decode_combt(t(p.codes1), t(p.codes2), t(p.lut), p.M, p.K, p.KV1, p.KV2, p.S)
+        if p.simt:
+            return O.simt_decode(t(p.codes1), t(p.lut), p.M, p.K, p.bits, p.vec)
+        return O.lut_tc_decode(t(p.codes1), t(p.lut), p.M, p.K, p.bits, p.vec)
+
+    for li, ly in enumerate(r.layers):
+        xin = rms(h, f(ly["norm1"]))
+        z = O.hadamard_ref(xin * f(ly["SU_qkv"])) / 64.0
+        acc = np.zeros(H + 2 * r.kvd)
+        for p, off in ly["qkv"]:
+            acc[off:off + p.M] = proj_W(p).astype(np.float64) @ z
+        qkv = acc * f(ly["W_qkv"]) * 64.0
+        q, k, v = qkv[:H].reshape(nh, D), qkv[H:H + r.kvd].reshape(nkv, D), qkv[H + r.kvd:].reshape(nkv, D)
+        ang = pos * r.inv_freq.double().cpu().numpy()
+        cos, sin = np.concatenate([np.cos(ang)] * 2), np.concatenate([np.sin(ang)] * 2)
+        rot = lambda a: np.concatenate([-a[..., D // 2:], a[..., :D // 2]], -1)
+        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
+        caches[li][0].append(k)
+        caches[li][1].append(v)
+        Kc, Vc = np.stack(caches[li][0], 0), np.stack(caches[li][1], 0)  # (T, nkv, D)
+        out = np.zeros((nh, D))
+        for hd in range(nh):
+            kv = hd // (nh // nkv)
+            s = Kc[:, kv] @ q[hd] / math.sqrt(D)
+            pm = np.exp(s - s.max())
+            pm /= pm.sum()
+            out[hd] = pm @ Vc[:, kv]
+        z = O.hadamard_ref(out.reshape(-1) * f(ly["SU_o"])) / 64.0
+        h = h + (proj_W(ly["o"]).astype(np.float64) @ z) * f(ly["W_o"]) * 64.0
+        xin = rms(h, f(ly["norm2"]))
+        z = O.hadamard_ref(xin * f(ly["SU_ug"])) / 64.0
+        acc = np.zeros(2 * I)
+        for p, off in ly["ug"]:
+            acc[off:off + p.M] = proj_W(p).astype(np.float64) @ z
+        ug = acc * f(ly["W_ug"]) * 64.0
+        up, gate = ug[:I], ug[I:]
+        act = gate / (1 + np.exp(-gate)) * up
+        z = O.hadamard_ref(act * f(ly["SU_dp"])) / 64.0
+        h = h + (proj_W(ly["down"]).astype(np.float64) @ z) * f(ly["W_dp"]) * 64.0
+    xf = rms(h, f(r.final_norm))
+    return h, f(r.lm_head) @ xf
+
+
+@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged"])
+def test_decode_step_matches_restatement(variant):
+    from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
+    shape = LlamaShape(hidden_size=512, intermediate_size=28 * 32, num_hidden_layers=2, num_attention_heads=8,
+                       num_key_value_heads=2, vocab_size=1024)
+    if variant == "uniform_merged":
+        qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 2
+    else:
+        qd = uniform_qdict(shape, "tcq_8_none_0.9")
+        qd["0_self_attn.k_proj"] = ("ldlq_1_6_none_1.0", "0")
+        qd["0_self_attn.v_proj"] = ("ldlq_1_6_none_1.0", "0")
+        qd["1_self_attn.q_proj"] = ("ldlq_2_6_none_1.0", "1")
+        qd["1_mlp.down_proj"] = ("tcomb_7_8_0.5_none_0.9", "0")
+        mi = [["merge_kv"], []]
+    r = DecodeRunner(shape, qd, mi, max_seq=16, seed=3)
+    caches = [([], []) for _ in r.layers]
+    tok = 5
+    r.reset(tok)
+    for step in range(3):
+        x0 = r.embed[tok].float().cpu().numpy()
+        _, logits_ref = _ref_layer_step(r, x0, step, caches)
+        r.step()
+        torch.cuda.synchronize()
+        logits = r.logits.cpu().numpy()
+        assert rel_l2(logits, logits_ref) <= 2e-2, (variant, step)  # fp16 residual stream vs float64 restatement
+        assert int(r.pos.item()) == step + 1
+        tok = int(r.token.item())
+        assert tok == int(np.argmax(logits))
+    eager = r.generate(4, token=7)  # graph replay reproduces the eager tokens
+    r.capture()
+    assert r.generate(4, token=7) == eager
+    assert r.launches_per_step > 0
