@@ -15,7 +15,7 @@
 
 namespace qp {
 
-constexpr int kDecThreads = 512;
+constexpr int kDecThreads = 1024;
 
 __device__ __forceinline__ float block_sum(float v, float *red) {
 #pragma unroll
@@ -47,49 +47,139 @@ __device__ __forceinline__ void zero_words(float *p, int count) {
     for (int i = threadIdx.x; i < count; i += blockDim.x) p[i] = 0.f;
 }
 
-// see header comment.  All pointers optional except x_out/h.  One CTA.
+__device__ __forceinline__ void zero_words4(float *p, int count) {
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    for (int i = threadIdx.x; i < count / 4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = (count & ~3) + threadIdx.x; i < count; i += blockDim.x) p[i] = 0.f;
+}
+
+__device__ __forceinline__ void unpack4(const uint2 u, float (&f)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
+    uint2 u;
+    *reinterpret_cast<__half2 *>(&u.x) = __floats2half2_rn(f[0], f[1]);
+    *reinterpret_cast<__half2 *>(&u.y) = __floats2half2_rn(f[2], f[3]);
+    return u;
+}
+// fp16(fp16(fp16(acc) * wscale) * s): the rounding points of `linear(x).half() * Wscale * scale`
+__device__ __forceinline__ float scaled_acc(float acc, float ws, __half hs) {
+    return __half2float(__hmul(__hmul(__float2half(acc), __float2half(ws)), hs));
+}
+
+// butterfly stages of element stride 1, 2 (registers) and 4..64 (warp shuffles) on a warp's 128 consecutive elements:
+// lane l holds elements 4l..4l+3.  Shared memory only sees strides >= 128, which are bank-conflict free.
+__device__ __forceinline__ void had_warp128(float (&y)[4]) {
+    const float a = y[0] + y[1], b = y[0] - y[1], c = y[2] + y[3], d = y[2] - y[3];
+    y[0] = a + c; y[1] = b + d; y[2] = a - c; y[3] = b - d;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const bool upper = (lane >> s) & 1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float o = __shfl_xor_sync(0xffffffffu, y[e], 1 << s);
+            y[e] = upper ? (o - y[e]) : (y[e] + o);
+        }
+    }
+}
+constexpr int kHadLh0 = 7;  // log2 of the first stride left for shared memory after had_warp128
+
+// Single-CTA fused glue.  Every thread owns CH chunks of 4 consecutive elements; ALL global loads of the kernel are issued
+// before the first dependent instruction (these kernels are pure latency: one L2 round trip instead of one per loop trip).
+// The first two butterfly stages run in registers, the rest in shared memory.
+template <int CH>
 __global__ void __launch_bounds__(kDecThreads, 1)
-fused_norm_had_kernel(__half *__restrict__ x_out, __half *__restrict__ h, int h_writeback,
-                      const float *__restrict__ acc, const __half *__restrict__ wscale, float acc_scale,
-                      const __half *__restrict__ norm_w, float eps, const __half *__restrict__ su, int n, int m, int Kf,
-                      float had_scale, int do_had, float *__restrict__ zero_ptr, int zero_count) {
+fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, const float *__restrict__ acc,
+                      const __half *__restrict__ wscale, float acc_scale, const __half *__restrict__ norm_w, float eps,
+                      const __half *__restrict__ su, int n, int m, int Kf, float had_scale, int do_had,
+                      float *__restrict__ zero_ptr, int zero_count) {
     extern __shared__ __align__(16) float v[];
     __shared__ float red[32];
     pdl_wait();
     pdl_launch_dependents();
-    if (zero_ptr) zero_words(zero_ptr, zero_count);
+    const int nch = n >> 2;
+    uint2 hv[CH], wv[CH], nv[CH], sv[CH];
+    float4 av[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        const bool ok = c < nch;
+        hv[j] = ok ? reinterpret_cast<const uint2 *>(h)[c] : make_uint2(0u, 0u);
+        av[j] = (ok && acc) ? reinterpret_cast<const float4 *>(acc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[j] = (ok && acc) ? reinterpret_cast<const uint2 *>(wscale)[c] : make_uint2(0u, 0u);
+        nv[j] = (ok && norm_w) ? reinterpret_cast<const uint2 *>(norm_w)[c] : make_uint2(0u, 0u);
+        sv[j] = (ok && su) ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    }
+    if (zero_ptr) zero_words4(zero_ptr, zero_count);
+    const __half hs = __float2half(acc_scale);
+    float y[CH][4];
     float ss = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        __half hv = h[i];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        unpack4(hv[j], y[j]);
         if (acc) {
-            const __half t = __hmul(__hmul(__float2half(acc[i]), wscale[i]), __float2half(acc_scale));
-            hv = __hadd(hv, t);
-            if (h_writeback) h[i] = hv;
+            float w4[4];
+            unpack4(wv[j], w4);
+            const float a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                y[j][e] = __half2float(__hadd(__float2half(y[j][e]), __float2half(scaled_acc(a4[e], w4[e], hs))));
+            if (h_writeback && c < nch) reinterpret_cast<uint2 *>(h)[c] = pack4(y[j]);
         }
-        const float f = __half2float(hv);
-        v[i] = f;
-        ss += f * f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss += y[j][e] * y[j][e];
     }
     if (norm_w) {
-        const float tot = block_sum(ss, red);
-        const float rstd = rsqrtf(tot / (float)n + eps);
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            // HF LlamaRMSNorm: weight * (x.float() * rstd).to(fp16)
-            const __half xn = __float2half(v[i] * rstd);
-            v[i] = __half2float(__hmul(norm_w[i], xn));
+        const float rstd = rsqrtf(block_sum(ss, red) / (float)n + eps);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            float w4[4];
+            unpack4(nv[j], w4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)  // HF LlamaRMSNorm: weight * (x.float() * rstd).to(fp16)
+                y[j][e] = __half2float(__hmul(__float2half(w4[e]), __float2half(y[j][e] * rstd)));
         }
     }
-    if (su) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] *= __half2float(su[i]);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        if (su) {
+            float s4[4];
+            unpack4(sv[j], s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[j][e] *= s4[e];
+        }
+        if (do_had) had_warp128(y[j]);  // strides 1..64 in registers / shuffles (a warp's chunks are 128 consecutive elements)
+        if (c < nch) {
+            if (do_had) reinterpret_cast<float4 *>(v)[c] = make_float4(y[j][0], y[j][1], y[j][2], y[j][3]);
+            else {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = y[j][e] * had_scale;
+                reinterpret_cast<uint2 *>(x_out)[c] = pack4(o);
+            }
+        }
     }
+    if (!do_had) return;
     __syncthreads();
-    if (do_had) hadamard_smem(v, n, m, Kf);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) x_out[i] = __float2half(v[i] * had_scale);
+    hadamard_smem(v, n, m, Kf, kHadLh0);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        if (c < nch) {
+            const float4 f = reinterpret_cast<const float4 *>(v)[c];
+            const float o[4] = {f.x * had_scale, f.y * had_scale, f.z * had_scale, f.w * had_scale};
+            reinterpret_cast<uint2 *>(x_out)[c] = pack4(o);
+        }
+    }
 }
 
 // acc = [up (I) | gate (I)] fp32 -> y = silu(gate)*up (fp16 rounding points as the reference graph) -> *su -> had -> x
+template <int CH>
 __global__ void __launch_bounds__(kDecThreads, 1)
 silu_mul_had_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, const __half *__restrict__ wscale,
                     float acc_scale, const __half *__restrict__ su, int I, int m, int Kf, float had_scale,
@@ -97,55 +187,91 @@ silu_mul_had_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, c
     extern __shared__ __align__(16) float v[];
     pdl_wait();
     pdl_launch_dependents();
-    if (zero_ptr) zero_words(zero_ptr, zero_count);
+    const int nch = I >> 2;
+    float4 au[CH], ag[CH];
+    uint2 wu[CH], wg[CH], sv[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        const bool ok = c < nch;
+        au[j] = ok ? reinterpret_cast<const float4 *>(acc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        ag[j] = ok ? reinterpret_cast<const float4 *>(acc + I)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        wu[j] = ok ? reinterpret_cast<const uint2 *>(wscale)[c] : make_uint2(0u, 0u);
+        wg[j] = ok ? reinterpret_cast<const uint2 *>(wscale + I)[c] : make_uint2(0u, 0u);
+        sv[j] = (ok && su) ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    }
+    if (zero_ptr) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
-    for (int i = threadIdx.x; i < I; i += blockDim.x) {
-        const __half up = __hmul(__hmul(__float2half(acc[i]), wscale[i]), hs);
-        const __half gate = __hmul(__hmul(__float2half(acc[I + i]), wscale[I + i]), hs);
-        const float g = __half2float(gate);
-        const __half act = __float2half(g / (1.f + __expf(-g)));
-        float y = __half2float(__hmul(act, up));
-        if (su) y *= __half2float(su[i]);
-        v[i] = y;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        float w_u[4], w_g[4], s4[4], y[4];
+        unpack4(wu[j], w_u);
+        unpack4(wg[j], w_g);
+        unpack4(sv[j], s4);
+        const float u4[4] = {au[j].x, au[j].y, au[j].z, au[j].w}, g4[4] = {ag[j].x, ag[j].y, ag[j].z, ag[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float up = scaled_acc(u4[e], w_u[e], hs), g = scaled_acc(g4[e], w_g[e], hs);
+            const __half act = __float2half(g / (1.f + __expf(-g)));
+            y[e] = __half2float(__hmul(act, __float2half(up)));
+            if (su) y[e] *= s4[e];
+        }
+        had_warp128(y);
+        if (c < nch) reinterpret_cast<float4 *>(v)[c] = make_float4(y[0], y[1], y[2], y[3]);
     }
     __syncthreads();
-    hadamard_smem(v, I, m, Kf);
-    for (int i = threadIdx.x; i < I; i += blockDim.x) x_out[i] = __float2half(v[i] * had_scale);
+    hadamard_smem(v, I, m, Kf, kHadLh0);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        if (c < nch) {
+            const float4 f = reinterpret_cast<const float4 *>(v)[c];
+            const float o[4] = {f.x * had_scale, f.y * had_scale, f.z * had_scale, f.w * had_scale};
+            reinterpret_cast<uint2 *>(x_out)[c] = pack4(o);
+        }
+    }
 }
 
-// One CTA per query head.  acc_qkv: fp32 [q (H*D) | k (Hkv*D) | v (Hkv*D)] raw GEMV sums; wscale same layout.
+// One CTA (256 threads) per query head.  acc_qkv: fp32 [q (H*D) | k (Hkv*D) | v (Hkv*D)] raw GEMV sums; wscale same layout.
 // RoPE (HF rotate_half convention, model/llama.py apply_rotary_pos_emb) with inv_freq table (D/2 floats, llama3 scaling
-// already applied by the host).  KV cache: fp16 [2][max_seq][Hkv][D] for this layer.  pos read from device memory.
-__global__ void __launch_bounds__(128, 1)
+// already applied by the host).  KV cache: fp16 [max_seq][Hkv][D] per layer.  pos read from device memory.
+// D = 128: a warp covers one cached position with one 8-byte load per lane; 8 positions are in flight per warp.
+constexpr int kAttnThreads = 256;
+__global__ void __launch_bounds__(kAttnThreads, 1)
 rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ acc_qkv, const __half *__restrict__ wscale,
                       float acc_scale, const float *__restrict__ inv_freq, __half *__restrict__ kcache,
                       __half *__restrict__ vcache, const int *__restrict__ pos_ptr, int H, int Hkv, int D, int max_seq,
                       float *__restrict__ zero_ptr, int zero_count) {
-    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | scores[max_seq]
+    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[2][D] | scores[max_seq]
     __shared__ float red[32];
-    float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *sc = sm + 3 * D;
+    float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *part = sm + 3 * D, *sc = sm + 5 * D;
     pdl_wait();
     pdl_launch_dependents();
     const int head = blockIdx.x, kvh = head / (H / Hkv);
     const int pos = *pos_ptr;
-    if (zero_ptr && blockIdx.x == 0) zero_words(zero_ptr, zero_count);
+    if (zero_ptr && blockIdx.x == 0) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
     const int d = threadIdx.x;
     if (d < D) {
-        auto val = [&](int idx) { return __half2float(__hmul(__hmul(__float2half(acc_qkv[idx]), wscale[idx]), hs)); };
         const int half = D / 2;
         const int pd = d < half ? d + half : d - half;
+        const int iq = head * D, ik = H * D + kvh * D, iv = (H + Hkv) * D + kvh * D;
+        // all loads first
+        const float aq = acc_qkv[iq + d], aqp = acc_qkv[iq + pd], ak = acc_qkv[ik + d], akp = acc_qkv[ik + pd], av = acc_qkv[iv + d];
+        const float wq = __half2float(wscale[iq + d]), wqp = __half2float(wscale[iq + pd]), wk = __half2float(wscale[ik + d]),
+                    wkp = __half2float(wscale[ik + pd]), wv = __half2float(wscale[iv + d]);
+        const float fr = inv_freq[d % half];
         const float sgn = d < half ? -1.f : 1.f;
         double snd, csd;  // precise range reduction (the build uses --use_fast_math)
-        sincos((double)pos * (double)inv_freq[d % half], &snd, &csd);
-        const float sn = (float)snd, cs = (float)csd;
+        sincos((double)pos * (double)fr, &snd, &csd);
         // fp16 rounding of cos/sin and of the products as the fp16 reference graph does
-        const float c16 = __half2float(__float2half(cs)), s16 = __half2float(__float2half(sn));
-        const float qa = val(head * D + d), qb = val(head * D + pd);
-        const float ka = val(H * D + kvh * D + d), kb = val(H * D + kvh * D + pd);
+        const float c16 = __half2float(__float2half((float)csd)), s16 = __half2float(__float2half((float)snd));
+        const float qa = scaled_acc(aq, wq, hs), qb = scaled_acc(aqp, wqp, hs);
+        const float ka = scaled_acc(ak, wk, hs), kb = scaled_acc(akp, wkp, hs);
         q[d] = __half2float(__float2half(qa * c16 + sgn * qb * s16));
         const __half kr = __float2half(ka * c16 + sgn * kb * s16);
-        const __half vv = __float2half(val((H + Hkv) * D + kvh * D + d));
+        const __half vv = __float2half(scaled_acc(av, wv, hs));
         kn[d] = __half2float(kr);
         vn[d] = __half2float(vv);
         if (head % (H / Hkv) == 0) {  // one CTA of the group appends to the cache
@@ -155,19 +281,44 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     __syncthreads();
     const float scale = rsqrtf((float)D);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    // scores over cached positions [0, pos) + the new token (from shared memory, not the cache: no cross-CTA race)
-    for (int t = warp; t <= pos; t += nw) {
-        float s = 0.f;
-        if (t < pos) {
-            const __half *kr = kcache + ((size_t)t * Hkv + kvh) * D;
-            for (int i = lane; i < D; i += 32) s += q[i] * __half2float(kr[i]);
-        } else {
-            for (int i = lane; i < D; i += 32) s += q[i] * kn[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kAttnThreads / 32;
+    // scores over cached positions [0, pos): lane owns dims 4*lane..+3 (D = 128) -- generic D handled by the strided loop
+    if (D == 128) {
+        const float4 q4 = reinterpret_cast<const float4 *>(q)[lane];
+        for (int t0 = warp; t0 < pos; t0 += nw * 8) {
+            uint2 kv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nw;
+                kv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nw;
+                float k4[4];
+                unpack4(kv[u], k4);
+                float s = q4.x * k4[0] + q4.y * k4[1] + q4.z * k4[2] + q4.w * k4[3];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && t < pos) sc[t] = s * scale;
+            }
         }
+    } else {
+        for (int t = warp; t < pos; t += nw) {
+            const __half *kr = kcache + ((size_t)t * Hkv + kvh) * D;
+            float s = 0.f;
+            for (int i = lane; i < D; i += 32) s += q[i] * __half2float(kr[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sc[t] = s * scale;
+        }
+    }
+    if (warp == 0) {  // the new token, from shared memory (not the cache: no cross-CTA race)
+        float s = 0.f;
+        for (int i = lane; i < D; i += 32) s += q[i] * kn[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sc[t] = s * scale;
+        if (lane == 0) sc[pos] = s * scale;
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -181,11 +332,31 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     sum = block_sum(sum, red);
     __syncthreads();
-    if (d < D) {
+    // output: two halves of the positions per dim, 8 loads in flight
+    const int dd = threadIdx.x % D, part_id = threadIdx.x / D, nparts = (kAttnThreads / D) >= 2 ? 2 : 1;
+    if (part_id < nparts) {
         float o = 0.f;
-        for (int t = 0; t < pos; ++t) o += sc[t] * __half2float(vcache[((size_t)t * Hkv + kvh) * D + d]);
-        o += sc[pos] * vn[d];
-        attn_out[head * D + d] = __float2half(o / sum);
+        for (int t0 = part_id; t0 < pos; t0 += nparts * 8) {
+            __half vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nparts;
+                vv[u] = (t < pos) ? vcache[((size_t)t * Hkv + kvh) * D + dd] : __float2half(0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nparts;
+                if (t < pos) o += sc[t] * __half2float(vv[u]);
+            }
+        }
+        if (part_id == 0) o += sc[pos] * vn[dd];
+        part[part_id * D + dd] = o;
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+        float o = part[threadIdx.x];
+        if (nparts > 1) o += part[D + threadIdx.x];
+        attn_out[head * D + threadIdx.x] = __float2half(o / sum);
     }
 }
 
@@ -310,6 +481,7 @@ __global__ void step_advance_kernel(int *pos, int *history, const int *token, in
 using namespace qp;
 
 static int had_dims(int n, int &m, int &Kf) {
+    QP_CHECK_ARG(n % 128 == 0, "Hadamard size %d must be a multiple of 128 for the fused kernels", n);
     Kf = 1;
     m = n;
     if ((n & (n - 1)) != 0) {
@@ -317,6 +489,7 @@ static int had_dims(int n, int &m, int &Kf) {
         Kf = 28;
         m = n / 28;
     }
+    QP_CHECK_ARG(m >= 128, "Hadamard block %d < 128 is not supported by the fused decode kernels (use qp_hadamard)", m);
     return QP_OK;
 }
 
@@ -330,15 +503,21 @@ extern "C" int qp_fused_norm_had(void *x_out_f16, void *h_f16, int h_writeback, 
     if (rc != QP_OK && do_had) return rc;
     const size_t smem = (size_t)n * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "n = %d too large", n);
-    static bool configured = false;
-    if (!configured) {
-        QP_CUDA(cudaFuncSetAttribute(fused_norm_had_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-        configured = true;
+    QP_CHECK_ARG(n % 4 == 0 && n <= 8 * 4 * kDecThreads, "n = %d unsupported (needs n %% 4 == 0, n <= 32768)", n);
+    const int ch = (n / 4 + kDecThreads - 1) / kDecThreads;
+    void (*kern)(__half *, __half *, int, const float *, const __half *, float, const __half *, float, const __half *, int,
+                 int, int, float, int, float *, int) =
+        ch <= 1 ? fused_norm_had_kernel<1> : ch <= 2 ? fused_norm_had_kernel<2> : ch <= 4 ? fused_norm_had_kernel<4>
+                                                                                       : fused_norm_had_kernel<8>;
+    static bool configured[4] = {false, false, false, false};
+    const int ki = ch <= 1 ? 0 : ch <= 2 ? 1 : ch <= 4 ? 2 : 3;
+    if (!configured[ki]) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
+        configured[ki] = true;
     }
-    QP_CUDA(launch_pdl(fused_norm_had_kernel, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16,
-                       (__half *)h_f16, h_writeback, acc, (const __half *)wscale_f16, acc_scale,
-                       (const __half *)norm_w_f16, eps, (const __half *)su_f16, n, m, Kf, had_scale, do_had, zero_ptr,
-                       zero_count));
+    QP_CUDA(launch_pdl(kern, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16, (__half *)h_f16,
+                       h_writeback, acc, (const __half *)wscale_f16, acc_scale, (const __half *)norm_w_f16, eps,
+                       (const __half *)su_f16, n, m, Kf, had_scale, do_had, zero_ptr, zero_count));
     return check_launch("fused_norm_had");
 }
 
@@ -350,13 +529,19 @@ extern "C" int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *ws
     if (rc != QP_OK) return rc;
     const size_t smem = (size_t)I * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "I = %d too large", I);
-    static bool configured = false;
-    if (!configured) {
-        QP_CUDA(cudaFuncSetAttribute(silu_mul_had_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-        configured = true;
+    QP_CHECK_ARG(I % 4 == 0 && I <= 8 * 4 * kDecThreads, "I = %d unsupported", I);
+    const int ch = (I / 4 + kDecThreads - 1) / kDecThreads;
+    void (*kern)(__half *, const float *, const __half *, float, const __half *, int, int, int, float, float *, int) =
+        ch <= 1 ? silu_mul_had_kernel<1> : ch <= 2 ? silu_mul_had_kernel<2> : ch <= 4 ? silu_mul_had_kernel<4>
+                                                                                     : silu_mul_had_kernel<8>;
+    static bool configured[4] = {false, false, false, false};
+    const int ki = ch <= 1 ? 0 : ch <= 2 ? 1 : ch <= 4 ? 2 : 3;
+    if (!configured[ki]) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
+        configured[ki] = true;
     }
-    QP_CUDA(launch_pdl(silu_mul_had_kernel, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16,
-                       acc, (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, m, Kf, had_scale, zero_ptr,
+    QP_CUDA(launch_pdl(kern, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16, acc,
+                       (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, m, Kf, had_scale, zero_ptr,
                        zero_count));
     return check_launch("silu_mul_had");
 }
@@ -365,15 +550,15 @@ extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const
                                  const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H,
                                  int Hkv, int D, int max_seq, float *zero_ptr, int zero_count, void *stream) {
     QP_CHECK_ARG(attn_out_f16 && acc_qkv && wscale_f16 && inv_freq && kcache_f16 && vcache_f16 && pos_ptr, "NULL pointer");
-    QP_CHECK_ARG(D <= 128 && D % 2 == 0 && H % Hkv == 0, "unsupported head geometry H=%d Hkv=%d D=%d", H, Hkv, D);
-    const size_t smem = (size_t)(3 * D + max_seq) * 4;
+    QP_CHECK_ARG(D <= 128 && D % 2 == 0 && H % Hkv == 0 && kAttnThreads % D == 0, "unsupported head geometry H=%d Hkv=%d D=%d", H, Hkv, D);
+    const size_t smem = (size_t)(5 * D + max_seq) * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "max_seq = %d too large for the single-pass attention kernel", max_seq);
     static bool configured = false;
     if (!configured) {
         QP_CUDA(cudaFuncSetAttribute(rope_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
         configured = true;
     }
-    QP_CUDA(launch_pdl(rope_attention_kernel, dim3(H), dim3(128), smem, (cudaStream_t)stream, (__half *)attn_out_f16,
+    QP_CUDA(launch_pdl(rope_attention_kernel, dim3(H), dim3(kAttnThreads), smem, (cudaStream_t)stream, (__half *)attn_out_f16,
                        acc_qkv, (const __half *)wscale_f16, acc_scale, inv_freq, (__half *)kcache_f16,
                        (__half *)vcache_f16, pos_ptr, H, Hkv, D, max_seq, zero_ptr, zero_count));
     return check_launch("rope_attention");

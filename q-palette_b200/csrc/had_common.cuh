@@ -5,54 +5,22 @@
 
 namespace qp {
 
-// the reference's 28x28 Hadamard matrix (lib/utils/matmul_had.py:261 get_had28) is Paley type II for q = 13:
-// H = [[S+I, S-I],[S-I, -S-I]], S = bordered Jacobsthal matrix of GF(13).  Built at compile time; row r of the table is
-// the sign mask of H[r][:] (bit j set <=> H[r][j] = -1).  H is symmetric, so H^T = H.
-struct Had28 {
-    uint32_t neg[28];
-};
-constexpr int legendre13(int x) {
-    x = ((x % 13) + 13) % 13;
-    if (x == 0) return 0;
-    for (int y = 1; y < 13; ++y)
-        if ((y * y) % 13 == x) return 1;
-    return -1;
-}
-constexpr int sval(int i, int j) {  // S, 14 x 14
-    if (i == 0 && j == 0) return 0;
-    if (i == 0 || j == 0) return 1;
-    return legendre13((j - 1) - (i - 1));
-}
-constexpr int had28_entry(int r, int c) {
-    const int i = r % 14, j = c % 14;
-    const int s = sval(i, j), d = (i == j) ? 1 : 0;
-    if (r < 14 && c < 14) return s + d;
-    if (r >= 14 && c >= 14) return -s - d;
-    return s - d;
-}
-constexpr Had28 make_had28() {
-    Had28 h = {};
-    for (int r = 0; r < 28; ++r) {
-        uint32_t m = 0;
-        for (int c = 0; c < 28; ++c)
-            if (had28_entry(r, c) < 0) m |= (1u << c);
-        h.neg[r] = m;
-    }
-    return h;
-}
-static __constant__ Had28 c_had28 = make_had28();
+// The reference's 28x28 Hadamard matrix (lib/utils/matmul_had.py:261 get_had28) is Paley type II for q = 13:
+// H = [[S+I, S-I],[S-I, -S-I]], S = bordered Jacobsthal matrix of GF(13) (checked bit-for-bit against get_had28() through
+// the golden fixture).  H is symmetric, so H^T = H.
+constexpr int kHadThreads = 1024;
 
-constexpr int kHadThreads = 512;
-
-template <int R>  // 2^R-point butterfly on registers, stride h in shared memory
-__device__ __forceinline__ void fwht_pass(float *v, int n, int h) {
+// 2^R-point butterflies held in registers, element stride h = 2^lh in shared memory (power of two: no div/mod)
+template <int R>
+__device__ __forceinline__ void fwht_pass(float *v, int n, int lh) {
     constexpr int P = 1 << R;
-    for (int idx = threadIdx.x; idx < n / P; idx += blockDim.x) {
-        const int low = idx % h, hi = idx / h;
-        float *base = v + (size_t)hi * P * h + low;
+    const int h = 1 << lh;
+    for (int idx = threadIdx.x; idx < (n >> R); idx += blockDim.x) {
+        const int low = idx & (h - 1), hi = idx >> lh;
+        float *base = v + ((hi << (R + lh)) | low);
         float r[P];
 #pragma unroll
-        for (int k = 0; k < P; ++k) r[k] = base[k * h];
+        for (int k = 0; k < P; ++k) r[k] = base[k << lh];
 #pragma unroll
         for (int s = 1; s < P; s <<= 1) {
 #pragma unroll
@@ -65,39 +33,64 @@ __device__ __forceinline__ void fwht_pass(float *v, int n, int h) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < P; ++k) base[k * h] = r[k];
+        for (int k = 0; k < P; ++k) base[k << lh] = r[k];
     }
 }
 
+// y = S x for the 14x14 bordered Jacobsthal matrix of GF(13): S[0][0]=0, S[0][j]=S[j][0]=1, S[1+i][1+j]=chi(j-i)
+__device__ __forceinline__ void jacobsthal14(const float (&x)[14], float (&y)[14]) {
+    constexpr int chi[13] = {0, 1, -1, 1, 1, -1, -1, -1, -1, 1, 1, -1, 1};  // Legendre symbol mod 13 (squares 1,3,4,9,10,12)
+    float s0 = 0.f;
+#pragma unroll
+    for (int j = 1; j < 14; ++j) s0 += x[j];
+    y[0] = s0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        float s = x[0];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int c = chi[(j - i + 13) % 13];
+            if (c > 0) s += x[1 + j];
+            else if (c < 0) s -= x[1 + j];
+        }
+        y[1 + i] = s;
+    }
+}
 
-// in-place (hadK^T (x) H_m) on v[n] (shared memory, fp32), n = Kf*m, m = 2^k, Kf in {1, 28}; ends with a barrier
-__device__ __forceinline__ void hadamard_smem(float *v, int n, int m, int Kf) {
-    int h = 1;
-    while (h < m) {
-        if (h * 8 <= m) {
-            fwht_pass<3>(v, n, h);
-            h *= 8;
-        } else if (h * 4 <= m) {
-            fwht_pass<2>(v, n, h);
-            h *= 4;
+// in-place (hadK^T (x) H_m) on v[n] (shared memory, fp32), n = Kf*m, m = 2^k, Kf in {1, 28}; ends with a barrier.
+// The 28x28 factor is applied through its Paley structure H = [[S+I, S-I],[S-I, -S-I]] (~400 flops per column instead
+// of 784); it is symmetric, so H^T = H.
+__device__ __forceinline__ void hadamard_smem(float *v, int n, int m, int Kf, int lh = 0) {  // lh: log2 of the first stride still to do
+    const int lm = 31 - __clz(m);
+    while (lh < lm) {
+        if (lh + 3 <= lm) {
+            fwht_pass<3>(v, n, lh);
+            lh += 3;
+        } else if (lh + 2 <= lm) {
+            fwht_pass<2>(v, n, lh);
+            lh += 2;
         } else {
-            fwht_pass<1>(v, n, h);
-            h *= 2;
+            fwht_pass<1>(v, n, lh);
+            lh += 1;
         }
         __syncthreads();
     }
     if (Kf == 28) {
         for (int c = threadIdx.x; c < m; c += blockDim.x) {
-            float col[28];
+            float u[14], w[14], su[14], sw[14];
 #pragma unroll
-            for (int j = 0; j < 28; ++j) col[j] = v[j * m + c];
+            for (int j = 0; j < 14; ++j) {
+                u[j] = v[j * m + c];
+                w[j] = v[(14 + j) * m + c];
+            }
+            jacobsthal14(u, su);
+            jacobsthal14(w, sw);
 #pragma unroll
-            for (int i = 0; i < 28; ++i) {
-                const uint32_t neg = c_had28.neg[i];  // H^T[i][j] = H[j][i] = H[i][j] (symmetric)
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < 28; ++j) s += ((neg >> j) & 1u) ? -col[j] : col[j];
-                v[i * m + c] = s;  // column c is private to this thread
+            for (int j = 0; j < 14; ++j) {
+                v[j * m + c] = (su[j] + u[j]) + (sw[j] - w[j]);          // (S+I)u + (S-I)w
+                v[(14 + j) * m + c] = (su[j] - u[j]) - (sw[j] + w[j]);   // (S-I)u - (S+I)w
             }
         }
         __syncthreads();

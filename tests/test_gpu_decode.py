@@ -193,7 +193,7 @@ def _ref_layer_step(r, x_in_h, pos, caches):
 @pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged"])
 def test_decode_step_matches_restatement(variant):
     from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
-    shape = LlamaShape(hidden_size=512, intermediate_size=28 * 32, num_hidden_layers=2, num_attention_heads=8,
+    shape = LlamaShape(hidden_size=512, intermediate_size=28 * 128, num_hidden_layers=2, num_attention_heads=8,
                        num_key_value_heads=2, vocab_size=1024)
     if variant == "uniform_merged":
         qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 2
