@@ -15,8 +15,10 @@ Metric (BASELINE.json): bs=1 decode tokens/s of Llama-3.1-8B with every linear q
             model's 32 distinct down_proj buffers (764 MB > L2), algorithmic bytes / time vs the measured HBM peak
   cpu_baseline / --impl reference: the reference's dequantize->matvec path restated in C (oracle/qp_cref.c, all host
             threads) on a bounded sample, extrapolated to tokens/s
-N > 1: the same model row-sharded over N GPUs (zero-copy row slices of the packed weights, NCCL all-gather at the four
-layer boundaries); total work is fixed, so scaling = "strong".  `--parallel replicas` runs N independent replicas instead.
+N > 1 (default `--parallel replicas`): N independent bs=1 decode streams, one per GPU, no data-path collective (decode
+requests are independent units) -> scaling = "weak".  `--parallel tp` row-shards every layer over the N GPUs instead
+(zero-copy row slices of the packed weights, NCCL all-gather at the four layer boundaries; scaling = "strong"); at bs=1 its
+128 collectives per token cost more than the sharding saves for the 8B model (DESIGN.md has the measured table).
 """
 import argparse
 import ctypes
@@ -178,7 +180,8 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"])
+    ap.add_argument("--parallel", default="replicas", choices=["tp", "replicas"],
+                    help="N > 1: independent bs=1 decode streams per GPU (default, weak scaling) or row-sharded tensor parallel")
     ap.add_argument("--workload", default="8b", choices=["8b", "70b"])
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (invalid as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -336,7 +339,12 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # tearing the NCCL communicator down while captured graphs still reference it can hang: finish, flush and leave
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

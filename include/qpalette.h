@@ -125,6 +125,36 @@ int qp_embed(void *h_f16, const void *table_f16, const int *token, int n, void *
 int qp_step_advance(int *pos, int *history, const int *token, int max_hist, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * GEMV with the activation-side glue fused into its prologue (bs = 1): every CTA of the GEMV computes
+ *     h' = src + fp16(acc)*wscale*acc_scale   (optional residual add; CTA 0 stores h' to h_out_f16, which must not alias src)
+ *     y  = RMSNorm(h', norm_w, eps)            (optional)
+ *     x  = fp16(Hadamard(y * su) * had_scale)  (su optional)
+ * itself while its first weight loads are in flight, then runs out += decode(W) x (out must be pre-zeroed / hold the
+ * value to add to).  x_out_f16 (optional) receives x for sibling projections; zero1/zero2 name fp32 buffers to clear for
+ * LATER launches (they must not be read or written by this one).  Replaces a qp_fused_norm_had launch + the x staging.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct qp_xprod {
+    const void *src_f16;
+    void *h_out_f16;
+    const float *acc;
+    const void *wscale_f16;
+    float acc_scale;
+    const void *norm_w_f16;
+    float eps;
+    const void *su_f16;
+    float had_scale;
+    void *x_out_f16;
+    float *zero1;
+    int zero1_count;
+    float *zero2;
+    int zero2_count;
+} qp_xprod;
+int qp_tcq_gemv_fused(float *out, const void *codes1, const void *codes2, const qp_xprod *xp, const void *tlut_f16,
+                      int M, int K, int S, int KV1, int KV2, int split_mode, int part1, void *stream);
+int qp_lut_gemv_fused(float *out, const void *codes, const qp_xprod *xp, const void *lut_f16, int M, int K, int bits,
+                      int vec_sz, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * host-buffer variant used for end-to-end timing: x_host (bs,K) fp16 pinned/pageable host memory, out_host (bs,M)
  * fp32 host memory; x_dev/out_dev are device scratch buffers of the same sizes.  Copies run on `stream`; the caller
  * synchronises the stream before reading out_host.

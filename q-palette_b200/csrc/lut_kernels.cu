@@ -9,6 +9,7 @@
 // E = 11 / 12 only 16 / 8 copies fit in 128 KiB.
 #include "gemv_common.cuh"
 #include "lut_bits.cuh"
+#include "xprod.cuh"
 
 namespace qp {
 
@@ -81,9 +82,10 @@ struct LutDecoder {
 template <int E, bool SPLIT>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const uint32_t *__restrict__ x32,
-                const void *__restrict__ lut, int r_single, int M, int K, int bs) {
+                const void *__restrict__ lut, int r_single, int M, int K, int bs, XProd prod) {
     using T = LutTable<E, SPLIT>;
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ float red[32];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);  // compact lut copy
     uint32_t *xs = lc + lut_compact_words(E, r_single);
@@ -97,7 +99,8 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     __syncthreads();
     lut_build_table<E, SPLIT>(tab, lc, r_single);
     pdl_wait();
-    stage_x(xs, x32, K, bs);
+    if (prod.mode == 0) stage_x(xs, x32, K, bs);
+    else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
     __syncthreads();
     pdl_launch_dependents();
     const uint8_t *tab_addr_lane = smem + ((lane & T::kLaneMask) << 2);
@@ -124,18 +127,20 @@ lut_dequant_kernel(PackSegment seg, RunSplit split, __half *__restrict__ W, cons
 
 template <int E, bool SPLIT>
 static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const void *lut, int r_single, int M, int K,
-                           int bs, cudaStream_t st) {
+                           int bs, const XProd &prod, cudaStream_t st) {
     using T = LutTable<E, SPLIT>;
     auto kern = lut_gemv_kernel<E, SPLIT>;
     static bool configured = false;
     if (!configured) {
-        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
         configured = true;
     }
-    const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2;
+    const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2 +
+                        (prod.mode ? (size_t)K * 4 : 0);
+    QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg,
                        make_split((long)seg.strips * seg.ksuper, sm_count()), out, (const uint32_t *)x, lut,
-                       r_single, M, K, bs));
+                       r_single, M, K, bs, prod));
     return check_launch("lut_gemv");
 }
 
@@ -194,9 +199,9 @@ static int lut_table_bytes(int bits, int vec_sz) {
     }
 
 static int dispatch_lut_gemv(int bits, int vec_sz, PackSegment seg, float *out, const void *x, const void *lut, int M,
-                             int K, int bs, cudaStream_t st) {
+                             int K, int bs, const XProd &prod, cudaStream_t st) {
     const int r_single = vec_sz == 1 ? bits : 0;
-    QP_LUT_DISPATCH(launch_lut_gemv, seg, out, x, lut, r_single, M, K, bs, st)
+    QP_LUT_DISPATCH(launch_lut_gemv, seg, out, x, lut, r_single, M, K, bs, prod, st)
     return fail(QP_ERR_ARG, "unsupported LUT configuration bits=%d vec_sz=%d", bits, vec_sz);
 }
 
@@ -227,7 +232,7 @@ extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, con
     int rc = lut_check(codes, M, K, bits, vec_sz);
     if (rc != QP_OK) return rc;
     if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
-    const size_t avail = (size_t)kMaxSmem - (size_t)lut_table_bytes(bits, vec_sz) - 16 * 1024;
+    const size_t avail = (size_t)kMaxSmem - 256 - (size_t)lut_table_bytes(bits, vec_sz) - 16 * 1024;
     int chunk = (int)(avail / ((size_t)K * 2));
     QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
     if (chunk > bs) chunk = bs;
@@ -235,8 +240,9 @@ extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, con
     PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
     for (int b0 = 0; b0 < bs; b0 += chunk) {
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
+        XProd none = {};
         rc = dispatch_lut_gemv(bits, vec_sz, seg, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, lut_f16,
-                               M, K, nb, st);
+                               M, K, nb, none, st);
         if (rc != QP_OK) return rc;
     }
     return QP_OK;
@@ -250,4 +256,48 @@ extern "C" int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f1
     if (rc != QP_OK) return rc;
     PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
     return dispatch_lut_dequant(bits, vec_sz, seg, (__half *)W_f16, lut_f16, K, st);
+}
+
+// ---- fused prologue entry point -------------------------------------------------------------------------------------
+int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
+    QP_CHECK_ARG(u->src_f16 != nullptr, "xprod.src_f16 is NULL");
+    QP_CHECK_ARG(!u->acc || u->wscale_f16, "xprod.acc given without wscale");
+    QP_CHECK_ARG(K % 128 == 0, "fused prologue needs K %% 128 == 0 (K = %d)", K);
+    int Kf = 1, m = K;
+    if ((K & (K - 1)) != 0) {
+        QP_CHECK_ARG(K % 28 == 0 && (((K / 28) & (K / 28 - 1)) == 0), "Hadamard size %d is neither 2^k nor 28*2^k", K);
+        Kf = 28;
+        m = K / 28;
+    }
+    QP_CHECK_ARG(m >= 128, "Hadamard block %d < 128", m);
+    QP_CHECK_ARG(K <= 5 * 4 * kGemvThreads, "K = %d too large for the fused prologue", K);
+    p.mode = 1;
+    p.src = (const __half *)u->src_f16;
+    p.h_out = (__half *)u->h_out_f16;
+    p.acc = u->acc;
+    p.wscale = (const __half *)u->wscale_f16;
+    p.acc_scale = u->acc_scale;
+    p.norm_w = (const __half *)u->norm_w_f16;
+    p.eps = u->eps;
+    p.su = (const __half *)u->su_f16;
+    p.had_scale = u->had_scale;
+    p.x_out = (__half *)u->x_out_f16;
+    p.zero1 = u->zero1;
+    p.zero1_count = u->zero1_count;
+    p.zero2 = u->zero2;
+    p.zero2_count = u->zero2_count;
+    p.m = m;
+    p.Kf = Kf;
+    return QP_OK;
+}
+
+extern "C" int qp_lut_gemv_fused(float *out, const void *codes, const qp_xprod *xp, const void *lut_f16, int M, int K,
+                                 int bits, int vec_sz, void *stream) {
+    QP_CHECK_ARG(out && xp && lut_f16, "NULL pointer argument");
+    int rc = lut_check(codes, M, K, bits, vec_sz);
+    if (rc != QP_OK) return rc;
+    XProd p;
+    if ((rc = qp_make_xprod(p, xp, K)) != QP_OK) return rc;
+    PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
+    return dispatch_lut_gemv(bits, vec_sz, seg, out, nullptr, lut_f16, M, K, 1, p, (cudaStream_t)stream);
 }

@@ -15,6 +15,7 @@
 #include "qp_common.cuh"
 #include "tcq_bits.cuh"
 #include "gemv_common.cuh"
+#include "xprod.cuh"
 
 namespace qp {
 
@@ -82,12 +83,18 @@ __device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *_
 template <int S>
 __device__ __forceinline__ uint32_t tcq_lookup(const uint8_t *tab_lane, uint32_t u) {
     using T = TcqTable<S>;
-    const uint32_t t = tcq_hash(u);
+    // hash t = u*(u+1) pre-shifted by kShift with two multiply-adds (fma pipe) instead of multiply + shift/add (alu pipe,
+    // which the extraction shifts and the mask already saturate): t << k = u * ((u << k) + (1 << k))
+#ifdef QP_HASH_ADD
+    const uint32_t t0 = tcq_hash(u);
+    const uint32_t ts = (T::kShift == 1) ? (t0 + t0) : (t0 << T::kShift);
+#else
+    const uint32_t ts = u * (u * (1u << T::kShift) + (1u << T::kShift));
+#endif
     // slot offset = hash bits [15-S, 15-S+kEntryBits) moved to [kStrideLog2, ...); tab_lane already carries the lane's
     // 4-byte column, so the address is base + offset with no further arithmetic
-    const uint32_t off = ((T::kShift == 1) ? (t + t) : (t << T::kShift)) & T::kMask;
-    uint32_t w = *reinterpret_cast<const uint32_t *>(tab_lane + off);
-    if (!T::kFold) w ^= (t & 0x8000u);
+    uint32_t w = *reinterpret_cast<const uint32_t *>(tab_lane + (ts & T::kMask));
+    if (!T::kFold) w ^= ((ts >> T::kShift) & 0x8000u);
     return w;
 }
 
@@ -123,8 +130,9 @@ using TcqSegment = PackSegment;
 template <int KVA, int KVB, int S>
 __global__ void __launch_bounds__(kTcqThreads, 1)
 tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
-                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs) {
+                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, XProd prod) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ float red[32];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     uint32_t *xs = reinterpret_cast<uint32_t *>(smem + TcqTable<S>::kBytes);
 
@@ -142,7 +150,8 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     QP_PHASE(2);
     pdl_wait();  // x (and out) are produced by the preceding kernel
     QP_PHASE(3);
-    stage_x(xs, x32, K, bs);
+    if (prod.mode == 0) stage_x(xs, x32, K, bs);
+    else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
     __syncthreads();
     QP_PHASE(4);
     pdl_launch_dependents();
@@ -222,18 +231,19 @@ static int make_segments(TcqLaunch &L, const void *codes1, const void *codes2, i
 
 template <int KVA, int KVB, int S>
 static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void *tlut, int M, int K, int bs,
-                       cudaStream_t st) {
+                       const XProd &prod, cudaStream_t st) {
     auto kern = tcq_gemv_kernel<KVA, KVB, S>;
-    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2;
+    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (prod.mode ? (size_t)K * 4 : 0);
+    QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
     static bool configured = false;  // per instantiation
     if (!configured) {
-        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
         configured = true;
     }
     const int nctas = sm_count();
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
                        make_split((long)L.a.strips * L.a.ksuper, nctas), make_split((long)L.b.strips * L.b.ksuper, nctas),
-                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs));
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
     return check_launch("tcq_gemv");
 }
 
@@ -272,29 +282,29 @@ static int launch_dequant(const TcqLaunch &L, __half *W, const void *tlut, int K
     break;
 
 static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, const void *tlut, int M, int K, int bs,
-                         cudaStream_t st) {
+                         const XProd &prod, cudaStream_t st) {
     if (L.kvb == 0) {
         switch (L.kva) {
-            case 2: QP_TCQ_SINGLE(launch_gemv, 2, L, out, x, tlut, M, K, bs, st)
-            case 3: QP_TCQ_SINGLE(launch_gemv, 3, L, out, x, tlut, M, K, bs, st)
-            case 4: QP_TCQ_SINGLE(launch_gemv, 4, L, out, x, tlut, M, K, bs, st)
-            case 5: QP_TCQ_SINGLE(launch_gemv, 5, L, out, x, tlut, M, K, bs, st)
-            case 6: QP_TCQ_SINGLE(launch_gemv, 6, L, out, x, tlut, M, K, bs, st)
-            case 7: QP_TCQ_SINGLE(launch_gemv, 7, L, out, x, tlut, M, K, bs, st)
-            case 8: QP_TCQ_SINGLE(launch_gemv, 8, L, out, x, tlut, M, K, bs, st)
-            case 9: QP_TCQ_SINGLE(launch_gemv, 9, L, out, x, tlut, M, K, bs, st)
-            case 10: QP_TCQ_SINGLE(launch_gemv, 10, L, out, x, tlut, M, K, bs, st)
+            case 2: QP_TCQ_SINGLE(launch_gemv, 2, L, out, x, tlut, M, K, bs, prod, st)
+            case 3: QP_TCQ_SINGLE(launch_gemv, 3, L, out, x, tlut, M, K, bs, prod, st)
+            case 4: QP_TCQ_SINGLE(launch_gemv, 4, L, out, x, tlut, M, K, bs, prod, st)
+            case 5: QP_TCQ_SINGLE(launch_gemv, 5, L, out, x, tlut, M, K, bs, prod, st)
+            case 6: QP_TCQ_SINGLE(launch_gemv, 6, L, out, x, tlut, M, K, bs, prod, st)
+            case 7: QP_TCQ_SINGLE(launch_gemv, 7, L, out, x, tlut, M, K, bs, prod, st)
+            case 8: QP_TCQ_SINGLE(launch_gemv, 8, L, out, x, tlut, M, K, bs, prod, st)
+            case 9: QP_TCQ_SINGLE(launch_gemv, 9, L, out, x, tlut, M, K, bs, prod, st)
+            case 10: QP_TCQ_SINGLE(launch_gemv, 10, L, out, x, tlut, M, K, bs, prod, st)
         }
     } else if (L.kvb == L.kva + 1) {
         switch (L.kva) {
-            case 2: QP_TCQ_PAIR(launch_gemv, 2, L, out, x, tlut, M, K, bs, st)
-            case 3: QP_TCQ_PAIR(launch_gemv, 3, L, out, x, tlut, M, K, bs, st)
-            case 4: QP_TCQ_PAIR(launch_gemv, 4, L, out, x, tlut, M, K, bs, st)
-            case 5: QP_TCQ_PAIR(launch_gemv, 5, L, out, x, tlut, M, K, bs, st)
-            case 6: QP_TCQ_PAIR(launch_gemv, 6, L, out, x, tlut, M, K, bs, st)
-            case 7: QP_TCQ_PAIR(launch_gemv, 7, L, out, x, tlut, M, K, bs, st)
-            case 8: QP_TCQ_PAIR(launch_gemv, 8, L, out, x, tlut, M, K, bs, st)
-            case 9: QP_TCQ_PAIR(launch_gemv, 9, L, out, x, tlut, M, K, bs, st)
+            case 2: QP_TCQ_PAIR(launch_gemv, 2, L, out, x, tlut, M, K, bs, prod, st)
+            case 3: QP_TCQ_PAIR(launch_gemv, 3, L, out, x, tlut, M, K, bs, prod, st)
+            case 4: QP_TCQ_PAIR(launch_gemv, 4, L, out, x, tlut, M, K, bs, prod, st)
+            case 5: QP_TCQ_PAIR(launch_gemv, 5, L, out, x, tlut, M, K, bs, prod, st)
+            case 6: QP_TCQ_PAIR(launch_gemv, 6, L, out, x, tlut, M, K, bs, prod, st)
+            case 7: QP_TCQ_PAIR(launch_gemv, 7, L, out, x, tlut, M, K, bs, prod, st)
+            case 8: QP_TCQ_PAIR(launch_gemv, 8, L, out, x, tlut, M, K, bs, prod, st)
+            case 9: QP_TCQ_PAIR(launch_gemv, 9, L, out, x, tlut, M, K, bs, prod, st)
         }
     } else {
         // arbitrary pair: two single-rate launches accumulating into the same output
@@ -303,9 +313,10 @@ static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, c
         b.a = L.b;
         b.kva = L.kvb;
         b.kvb = 0;
-        int rc = dispatch_gemv(a, S, out, x, tlut, M, K, bs, st);
+        QP_CHECK_ARG(prod.mode == 0, "the fused prologue needs a single-launch TCQ configuration");
+        int rc = dispatch_gemv(a, S, out, x, tlut, M, K, bs, prod, st);
         if (rc != QP_OK) return rc;
-        return dispatch_gemv(b, S, out, x, tlut, M, K, bs, st);
+        return dispatch_gemv(b, S, out, x, tlut, M, K, bs, prod, st);
     }
     return fail(QP_ERR_ARG, "unsupported TCQ configuration S=%d KV=(%d,%d)", S, L.kva, L.kvb);
 }
@@ -355,14 +366,15 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
     if ((rc = check_align(tlut_f16, 4, "tlut")) != QP_OK) return rc;
     // x lives in shared memory next to the 128 KiB codebook: process the batch in chunks that fit
-    const size_t avail = (size_t)kMaxSmem - 128 * 1024;
+    const size_t avail = (size_t)kMaxSmem - 256 - 128 * 1024;
     int chunk = (int)(avail / ((size_t)K * 2));
     QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
     if (chunk > bs) chunk = bs;
     if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
     for (int b0 = 0; b0 < bs; b0 += chunk) {
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
-        rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, st);
+        XProd none = {};
+        rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, none, st);
         if (rc != QP_OK) return rc;
     }
     return QP_OK;
@@ -399,3 +411,22 @@ extern "C" int qp_debug_phases(unsigned long long *host_out /* [256][8] */) {
     return QP_OK;
 }
 #endif
+
+// ---- fused prologue entry point -------------------------------------------------------------------------------------
+int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K);
+
+extern "C" int qp_tcq_gemv_fused(float *out, const void *codes1, const void *codes2, const qp_xprod *xp,
+                                 const void *tlut_f16, int M, int K, int S, int KV1, int KV2, int split_mode, int part1,
+                                 void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out && xp && tlut_f16, "NULL pointer argument");
+    QP_CHECK_ARG(S >= 9 && S <= 11, "tlut_bits S = %d not in {9,10,11}", S);
+    TcqLaunch L;
+    int rc = make_segments(L, codes1, codes2, M, K, KV1, KV2, split_mode, part1);
+    if (rc != QP_OK) return rc;
+    if ((rc = check_align(codes1, 16, "codes1")) != QP_OK) return rc;
+    if (codes2 && (rc = check_align(codes2, 16, "codes2")) != QP_OK) return rc;
+    XProd p;
+    if ((rc = qp_make_xprod(p, xp, K)) != QP_OK) return rc;
+    return dispatch_gemv(L, S, out, nullptr, tlut_f16, M, K, 1, p, st);
+}

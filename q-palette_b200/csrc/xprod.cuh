@@ -1,0 +1,176 @@
+// xprod.cuh -- "x producer": the activation-side glue of an incoherent quantized linear, computed INSIDE the GEMV
+// kernel's prologue by every CTA (redundantly: x is a few KB and L2 resident), so that
+//     h' = h + fp16(acc)*Wscale*s        (residual add of the previous projection's output, optional)
+//     y  = RMSNorm(h') * w                (optional)
+//     x  = fp16( Hadamard(y * SU) * scale )
+// costs no extra kernel launch and overlaps the first weight loads.  Replaces the standalone qp_fused_norm_had launch in
+// front of a GEMV (reference: lib/linear/incoherent_linear.py:76-108,324-338 + LlamaDecoderLayer residual/RMSNorm).
+// Only for bs = 1.  CTA 0 additionally stores h' (to a DIFFERENT buffer than h: other CTAs still read h) and, if asked, x.
+#pragma once
+#include "had_common.cuh"
+
+namespace qp {
+
+struct XProd {
+    int mode;                 // 0: x is given (plain staging); 1: produce x as described above
+    const __half *src;        // h (n)
+    __half *h_out;            // h' destination or NULL
+    const float *acc;         // optional fp32 accumulators (n) of the previous projection
+    const __half *wscale;     // its per-row scales (n)
+    float acc_scale;
+    const __half *norm_w;     // optional RMSNorm weight (n)
+    float eps;
+    const __half *su;         // optional signs (n)
+    float had_scale;
+    __half *x_out;            // optional copy of x in natural order (for sibling projections sharing x)
+    float *zero1;             // accumulators to clear for later launches (must not be touched by this launch)
+    int zero1_count;
+    float *zero2;
+    int zero2_count;
+    int m, Kf;                // Hadamard block / 28-factor of n
+};
+
+__device__ __forceinline__ float xp_block_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ void xp_unpack4(const uint2 u, float (&f)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+
+__device__ __forceinline__ void xp_had_warp128(float (&y)[4]) {
+    const float a = y[0] + y[1], b = y[0] - y[1], c = y[2] + y[3], d = y[2] - y[3];
+    y[0] = a + c; y[1] = b + d; y[2] = a - c; y[3] = b - d;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const bool upper = (lane >> s) & 1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float o = __shfl_xor_sync(0xffffffffu, y[e], 1 << s);
+            y[e] = upper ? (o - y[e]) : (y[e] + o);
+        }
+    }
+}
+
+__device__ __forceinline__ void xp_zero_slice(float *p, int count) {
+    if (!p) return;
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    const int n4 = count >> 2;
+    const int per = (n4 + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(n4, lo + per);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// produce x (n = K values) into xs in the B-fragment order stage_x() uses (bs = 1).  v: n floats of shared scratch.
+// CH = ceil(n / 4 / blockDim.x) chunks of 4 consecutive elements per thread.
+template <int CH>
+__device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n) {
+    const int nch = n >> 2, T = blockDim.x;
+    uint2 hv[CH], wv[CH], nv[CH], sv[CH];
+    float4 av[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        const bool ok = c < nch;
+        hv[j] = ok ? __ldg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
+        av[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const uint2 *>(p.wscale) + c) : make_uint2(0u, 0u);
+        nv[j] = (ok && p.norm_w) ? __ldg(reinterpret_cast<const uint2 *>(p.norm_w) + c) : make_uint2(0u, 0u);
+        sv[j] = (ok && p.su) ? __ldg(reinterpret_cast<const uint2 *>(p.su) + c) : make_uint2(0u, 0u);
+    }
+    xp_zero_slice(p.zero1, p.zero1_count);
+    xp_zero_slice(p.zero2, p.zero2_count);
+    const __half hs = __float2half(p.acc_scale);
+    float y[CH][4];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        xp_unpack4(hv[j], y[j]);
+        if (p.acc) {
+            float w4[4];
+            xp_unpack4(wv[j], w4);
+            const float a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half t = __hmul(__hmul(__float2half(a4[e]), __float2half(w4[e])), hs);
+                y[j][e] = __half2float(__hadd(__float2half(y[j][e]), t));
+            }
+            if (p.h_out && blockIdx.x == 0 && c < nch) {
+                uint2 u;
+                *reinterpret_cast<__half2 *>(&u.x) = __floats2half2_rn(y[j][0], y[j][1]);
+                *reinterpret_cast<__half2 *>(&u.y) = __floats2half2_rn(y[j][2], y[j][3]);
+                reinterpret_cast<uint2 *>(p.h_out)[c] = u;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss += y[j][e] * y[j][e];
+    }
+    if (p.norm_w) {
+        const float rstd = rsqrtf(xp_block_sum(ss, red) / (float)n + p.eps);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            float w4[4];
+            xp_unpack4(nv[j], w4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                y[j][e] = __half2float(__hmul(__float2half(w4[e]), __float2half(y[j][e] * rstd)));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        if (p.su) {
+            float s4[4];
+            xp_unpack4(sv[j], s4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[j][e] *= s4[e];
+        }
+        xp_had_warp128(y[j]);
+        if (c < nch) reinterpret_cast<float4 *>(v)[c] = make_float4(y[j][0], y[j][1], y[j][2], y[j][3]);
+    }
+    __syncthreads();
+    hadamard_smem(v, n, p.m, p.Kf, 7);
+    // fp16 x in B-fragment order: element i = 32*kh + 16*kl + 8*b + 2*q + e  ->  word ((kh*4 + q)*4 + kl*2 + b), half e
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        if (c < nch) {
+            const float4 f = reinterpret_cast<const float4 *>(v)[c];
+            const __half2 lo = __floats2half2_rn(f.x * p.had_scale, f.y * p.had_scale);
+            const __half2 hi = __floats2half2_rn(f.z * p.had_scale, f.w * p.had_scale);
+            const int i = c << 2;
+            const int kh = i >> 5, pp = i & 31, kl = pp >> 4, b = (pp >> 3) & 1, q = (pp >> 1) & 3;  // q in {0, 2}
+            uint32_t *d = xs + (kh * 16 + kl * 2 + b);
+            d[q * 4] = *reinterpret_cast<const uint32_t *>(&lo);
+            d[(q + 1) * 4] = *reinterpret_cast<const uint32_t *>(&hi);
+            if (p.x_out && blockIdx.x == 0) {
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t *>(&lo);
+                u.y = *reinterpret_cast<const uint32_t *>(&hi);
+                reinterpret_cast<uint2 *>(p.x_out)[c] = u;
+            }
+        }
+    }
+}
+
+// dispatch on the chunk count (n <= 15360 for 768 threads; larger n does not fit the shared-memory budget anyway)
+__device__ __forceinline__ void produce_x_dispatch(uint32_t *xs, float *v, float *red, const XProd &p, int n) {
+    const int ch = ((n >> 2) + blockDim.x - 1) / blockDim.x;
+    if (ch <= 2) produce_x<2>(xs, v, red, p, n);
+    else produce_x<5>(xs, v, red, p, n);  // host guarantees n <= 5 * 4 * blockDim.x
+}
+
+}  // namespace qp

@@ -37,9 +37,18 @@ SIGNATURES = {
     "qp_argmax": [_vp, _vp, _i, _vp, _vp],
     "qp_embed": [_vp, _vp, _vp, _i, _vp],
     "qp_step_advance": [_vp, _vp, _vp, _i, _vp],
+    "qp_tcq_gemv_fused": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "qp_lut_gemv_fused": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_tcq_gemv_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64}
+
+
+class XProd(ctypes.Structure):
+    """mirror of `qp_xprod` (include/qpalette.h)"""
+    _fields_ = [("src_f16", _vp), ("h_out_f16", _vp), ("acc", _vp), ("wscale_f16", _vp), ("acc_scale", _f),
+                ("norm_w_f16", _vp), ("eps", _f), ("su_f16", _vp), ("had_scale", _f), ("x_out_f16", _vp),
+                ("zero1", _vp), ("zero1_count", _i), ("zero2", _vp), ("zero2_count", _i)]
 
 
 class QPaletteError(RuntimeError):

@@ -22,6 +22,7 @@ import torch
 from . import _cabi
 from ._cabi import FLAG_ACCUMULATE, SPLIT_IN, SPLIT_NONE, check, lib
 from .linear.incoherent_linear import rope_inv_freq
+from .shard import shard_plan, shard_rows
 from .utils.mem_op import get_dummy_quant_results, get_quant_info
 
 
@@ -69,23 +70,9 @@ class _Proj:
                                        out_features=out_features)["linear_info"]
         self.M_full = out_features
         # row shard: keep rows [rank, rank+1) * M/world of every merged member (zero-copy slices: strip-major layout)
-        sizes = group_sizes or [out_features]
-        rows = []
-        base = 0
-        for s in sizes:
-            assert s % (32 * world) == 0, f"rows {s} not divisible into {world} shards of 32-row strips"
-            per = s // world
-            rows.append((base + rank * per, per))
-            base += s
-        self.M = sum(p for _, p in rows)
-
-        def shard(t):
-            """rows are strip-major in every packed layout: a block of 32*k rows is one contiguous flat range"""
-            flat = t.reshape(-1)
-            if world == 1 and len(rows) == 1:
-                return flat
-            per_row = flat.numel() // out_features
-            return torch.cat([flat[r0 * per_row:(r0 + n) * per_row] for r0, n in rows]).contiguous()
+        rows = shard_plan(group_sizes or [out_features], rank, world)
+        self.M = sum(n for _, n in rows)
+        shard = lambda t: shard_rows(t, out_features, rows)
 
         self.bufs = []
         if self.kind == "tcq_ldlq":
@@ -129,12 +116,30 @@ class _Proj:
                                 self.vec, FLAG_ACCUMULATE, stream))
 
 
+    def can_fuse(self):
+        return self.kind in ("tcq_ldlq", "combt_ldlq") or not self.simt
+
+    def launch_fused(self, out_ptr, xprod, stream):
+        """GEMV with the activation glue computed in its prologue (xprod: _cabi.XProd)"""
+        import ctypes
+        L = lib()
+        if self.kind in ("tcq_ldlq", "combt_ldlq"):
+            check(L.qp_tcq_gemv_fused(out_ptr, self.codes1.data_ptr(),
+                                      self.codes2.data_ptr() if self.codes2 is not None else None, ctypes.addressof(xprod),
+                                      self.lut.data_ptr(), self.M, self.K, self.S, self.KV1, self.KV2, self.split,
+                                      self.part1, stream))
+        else:
+            check(L.qp_lut_gemv_fused(out_ptr, self.codes1.data_ptr(), ctypes.addressof(xprod), self.lut.data_ptr(), self.M,
+                                      self.K, self.bits, self.vec, stream))
+
+
 class DecodeRunner:
     def __init__(self, shape=LLAMA31_8B, qdict=None, merge_info=None, max_seq=512, device="cuda", seed=0, rank=0,
-                 world=1, process_group=None, num_layers=None, random_scales=True):
+                 world=1, process_group=None, num_layers=None, random_scales=True, fused=True):
         self.shape, self.dev, self.rank, self.world, self.pg = shape, torch.device(device), rank, world, process_group
         self.L = num_layers or shape.num_hidden_layers
         self.max_seq = max_seq
+        self.fused = fused and world == 1   # GEMV-prologue fusion of the glue (single-GPU path)
         qdict = qdict or uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9")
         merge_info = merge_info or [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers
         g = torch.Generator(device=self.dev)
@@ -210,6 +215,7 @@ class DecodeRunner:
         z32 = dict(dtype=torch.float32, device=self.dev)
         Hq, Hk, Il = H // world, kvd // world, I // world
         self.h = torch.zeros(H, **f16)
+        self.h2 = torch.zeros(H, **f16)          # ping-pong partner of h for the fused prologues
         self.x_h = torch.zeros(H, **f16)
         self.x_i = torch.zeros(I, **f16)
         self.attn = torch.zeros(H, **f16)       # full attention output (all-gathered when sharded)
@@ -230,9 +236,75 @@ class DecodeRunner:
         self.lm_head_bytes = self.lm_head.numel() * 2
         self.launches_per_step = 0
         self._prepare_full_scales()
+        for ly in self.layers:  # the fused prologue needs one tensor-core-layout member per group
+            for grp in (ly["qkv"], [(ly["o"], 0)], ly["ug"]):
+                if not any(pr.can_fuse() for pr, _ in grp):
+                    self.fused = False
 
     # -----------------------------------------------------------------------------------------------------------------
     def _step(self):
+        if self.fused:
+            return self._step_fused()
+        return self._step_unfused()
+
+    def _step_fused(self):
+        """one decode step with residual/RMSNorm/sign/Hadamard fused into the GEMV prologues: per layer 4 GEMVs +
+        attention + SiLU*mul/Hadamard = 6 launches (9 unfused)."""
+        L, st = lib(), torch.cuda.current_stream().cuda_stream
+        sh, H, I = self.shape, self.H, self.I
+        n0 = _cabi.launch_count()
+        p = lambda t: t.data_ptr() if t is not None else None
+        s_h, s_i, S = 1.0 / (math.sqrt(H) * 64.0), 1.0 / (math.sqrt(I) * 64.0), 64.0
+        Hq, Hk = H, self.kvd
+        hc, ho = self.h, self.h2
+        check(L.qp_embed(p(hc), p(self.embed), p(self.token), H, st))
+
+        def xp(src, h_out=None, acc=None, ws=None, norm=None, su=None, scale=s_h, x_out=None, z1=None, z2=None):
+            return _cabi.XProd(p(src), p(h_out), p(acc), p(ws), S, p(norm), sh.rms_norm_eps, p(su), scale, p(x_out),
+                               p(z1), z1.numel() if z1 is not None else 0, p(z2), z2.numel() if z2 is not None else 0)
+
+        def run_group(projs, acc_buf, prod, x_buf):
+            """one projection computes x in its prologue (and publishes it if siblings need it); launch order inside a
+            group is free because the members write disjoint slices of the accumulator"""
+            lead = next(i for i, (pr, _) in enumerate(projs) if pr.can_fuse())
+            if len(projs) > 1:
+                prod.x_out_f16 = p(x_buf)
+            projs[lead][0].launch_fused(p(acc_buf) + 4 * projs[lead][1], prod, st)
+            for i, (proj, off) in enumerate(projs):
+                if i != lead:
+                    proj.launch(p(acc_buf) + 4 * off, p(x_buf), st)
+
+        prev = None
+        for ly in self.layers:
+            if prev is None:
+                prod = xp(hc, norm=ly["norm1"], su=ly["SU_qkv"], z1=self.acc_o, z2=self.acc_ug)
+            else:
+                prod = xp(hc, h_out=ho, acc=self.acc_dn, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"],
+                          z1=self.acc_o, z2=self.acc_ug)
+            run_group(ly["qkv"], self.acc_qkv, prod, self.x_h)
+            if prev is not None:
+                hc, ho = ho, hc
+            check(L.qp_rope_attention(p(self.attn), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
+                                      p(ly["vc"]), p(self.pos), sh.num_attention_heads, sh.num_key_value_heads,
+                                      sh.head_dim, self.max_seq, None, 0, st))
+            prod = xp(self.attn, su=ly["SU_o"], z1=self.acc_qkv, z2=self.acc_dn)
+            run_group([(ly["o"], 0)], self.acc_o, prod, self.x_h)
+            prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"])
+            run_group(ly["ug"], self.acc_ug, prod, self.x_h)
+            hc, ho = ho, hc
+            check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
+            ly["down"].launch(p(self.acc_dn), p(self.x_i), st)
+            prev = ly
+        check(L.qp_fused_norm_had(p(self.xf), p(hc), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
+                                  sh.rms_norm_eps, None, H, 1.0, 0, None, 0, st))
+        check(L.qp_gemv_f16(p(self.logits), p(self.lm_head), p(self.xf), sh.vocab_size, H, st))
+        check(L.qp_argmax(p(self.token), p(self.logits), sh.vocab_size, p(self.scratch), st))
+        check(L.qp_step_advance(p(self.pos), p(self.history), p(self.token), self.max_seq, st))
+        if hc is not self.h:  # an odd number of residual updates leaves the stream in h2: next step's embed targets self.h
+            pass
+        self.launches_per_step = _cabi.launch_count() - n0
+
+    def _step_unfused(self):
         """enqueue one decode step on the current stream (eager; also what gets captured into the graph)."""
         L, st = lib(), torch.cuda.current_stream().cuda_stream
         sh, H, I = self.shape, self.H, self.I

@@ -190,8 +190,9 @@ def _ref_layer_step(r, x_in_h, pos, caches):
     return h, f(r.lm_head) @ xf
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged"])
-def test_decode_step_matches_restatement(variant):
+def test_decode_step_matches_restatement(variant, fused):
     from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
     shape = LlamaShape(hidden_size=512, intermediate_size=28 * 128, num_hidden_layers=2, num_attention_heads=8,
                        num_key_value_heads=2, vocab_size=1024)
@@ -204,7 +205,8 @@ def test_decode_step_matches_restatement(variant):
         qd["1_self_attn.q_proj"] = ("ldlq_2_6_none_1.0", "1")
         qd["1_mlp.down_proj"] = ("tcomb_7_8_0.5_none_0.9", "0")
         mi = [["merge_kv"], []]
-    r = DecodeRunner(shape, qd, mi, max_seq=16, seed=3)
+    r = DecodeRunner(shape, qd, mi, max_seq=16, seed=3, fused=fused)
+    assert r.fused == fused
     caches = [([], []) for _ in r.layers]
     tok = 5
     r.reset(tok)
