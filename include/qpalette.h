@@ -69,6 +69,18 @@ int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, i
                    void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Fused dequantise + batched GEMM on tcgen05 tensor cores (TMEM accumulators), 1 <= bs <= 128 (meant for bs >= 16):
+ * out (bs, M) fp32 = x (bs, K) @ decode(W)^T without materialising W.  Same packed inputs as the GEMV entry points;
+ * needs M % 128 == 0, K % 64 == 0.  Replaces the reference's bs > 8 path `decompress_* + x @ dq.T`
+ * (lib/linear/tcq_linear.py:75-84, comb_linear.py:100-125,246-268, vq_linear.py:58-66).  qp_lut_gemm_tc covers vq2
+ * (2..12 bits) and SQ up to 5 bits; wider SQ falls back to qp_lut_dequant + GEMM on the host side.
+ * ------------------------------------------------------------------------------------------------------------- */
+int qp_tcq_gemm_tc(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16, int M,
+                   int K, int bs, int S, int KV1, int KV2, int split_mode, int part1, unsigned flags, void *stream);
+int qp_lut_gemm_tc(float *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs, int bits,
+                   int vec_sz, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * VQ / SQ in the SIMT layout (lib/quantizer/pack_op.py:288-335, quant_op.py:33-86).  out: fp16 (bs, M).
  * Replaces sq_pack_gemm.pack_gemm / pack_dequant (kernels/sq-cuda-kernels/gemm_routines.cu:474-722) and
  * vq_pack_gemm.vq_pack_gemm_* / vq_pack_dequant_* (kernels/vq-cuda-kernels/src/gemm_routines.cu:1913-2120).

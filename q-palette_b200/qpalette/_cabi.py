@@ -23,6 +23,8 @@ SIGNATURES = {
     "qp_device_sm_count": [],
     "qp_tcq_gemv": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
     "qp_tcq_dequant": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "qp_tcq_gemm_tc": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
+    "qp_lut_gemm_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_simt_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

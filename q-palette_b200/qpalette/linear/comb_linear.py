@@ -66,6 +66,10 @@ class _CombBase(nn.Module):
         x = inp.view(-1, self.in_features)
         if x.shape[0] <= 8:
             x = self._gemv(x)
+        elif ops.tc_gemm_supported(self.out_features, self.in_features) and self._part[0] % 128 == 0 and \
+                (self._split == SPLIT_OUT or self.KV[1] == self.KV[0] + 1):
+            x = ops.tcq_gemm_tc(self.trellis1, x, self.tlut, self.out_features, self.in_features, self.tlut_bits,
+                                self.KV[0], self.trellis2, self.KV[1], self._split, self._part[0])
         else:
             x = ops.batched_matmul(x, self.get_weight)
         return x.view(*inp.shape[:-1], self.out_features).to(inp.dtype)

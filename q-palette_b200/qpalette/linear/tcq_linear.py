@@ -38,6 +38,8 @@ class QTIPLinearTCQ(nn.Module):
         if bs <= 8:
             op = ops.resolve(f"decompress_gemm_tcq_{m}_{bs}_{k}_{self.tlut_bits}_{self.KV}")
             x = op(self.trellis, x, self.tlut)
+        elif ops.tc_gemm_supported(m, k):  # fused dequant + GEMM on tcgen05 (the reference: dequantise + cuBLAS)
+            x = ops.tcq_gemm_tc(self.trellis, x, self.tlut, m, k, self.tlut_bits, self.KV)
         else:
             x = ops.batched_matmul(x, lambda: ops.resolve(f"decompress_tcq_{self.tlut_bits}_{self.KV}")(
                 self.trellis, self.tlut, m, k))
