@@ -84,3 +84,36 @@ def test_llama_shape_large_batch():
     out = ops.tcq_gemm_tc(cuda(b1), cuda(x), cuda(tl), M, K, S, 6, cuda(b2), 7, SPLIT_IN, K // 2).cpu().numpy()
     ref = O.gemv_ref(O.tcq_decode_combt(b1, b2, tl, M, K, 6, 7, S), x)
     assert rel_l2(out, ref) <= 1e-3
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_many_row_blocks_plain_store(accumulate):
+    """enough 256-row blocks that K is not split: the epilogue stores (or read-modify-writes) instead of atomics"""
+    from qpalette import ops
+    rng = np.random.default_rng(31 + accumulate)
+    M, K, KV, S, bs = 256 * 120 + 128, 128, 5, 9, 24  # the last block has 128 rows
+    buf = rng.integers(0, 256, size=M * K * KV // 16, dtype=np.uint8)
+    tl = rand_tlut(rng, S)
+    x = rng.standard_normal((bs, K)).astype(np.float16)
+    ref = O.gemv_ref(O.tcq_decode(buf, tl, M, K, KV, S), x)
+    if accumulate:
+        base = rng.standard_normal((bs, M)).astype(np.float32)
+        out = ops.tcq_gemm_tc(cuda(buf), cuda(x), cuda(tl), M, K, S, KV, out=cuda(base), accumulate=True).cpu().numpy()
+        assert rel_l2(out - base, ref) <= 1e-3
+    else:
+        out = ops.tcq_gemm_tc(cuda(buf), cuda(x), cuda(tl), M, K, S, KV).cpu().numpy()
+        assert rel_l2(out, ref) <= 1e-3
+
+
+def test_split_k_accumulate():
+    """few row blocks (K split across CTAs, atomics) adding onto an existing output"""
+    from qpalette import ops
+    rng = np.random.default_rng(77)
+    M, K, R, bs = 512, 1024, 6, 100
+    lut = rng.standard_normal((1 << R, 2)).astype(np.float16)
+    buf = rng.integers(0, 256, size=M * K * R // 16, dtype=np.uint8)
+    x = rng.standard_normal((bs, K)).astype(np.float16)
+    ref = O.gemv_ref(O.lut_tc_decode(buf.view(np.int32), lut, M, K, R, 2), x)
+    base = rng.standard_normal((bs, M)).astype(np.float32)
+    out = ops.lut_gemm_tc(cuda(buf), cuda(x), cuda(lut), M, K, R, 2, out=cuda(base), accumulate=True).cpu().numpy()
+    assert rel_l2(out - base, ref) <= 1e-3
