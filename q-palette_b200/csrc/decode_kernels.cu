@@ -233,6 +233,110 @@ silu_mul_had_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, c
     }
 }
 
+// Multi-CTA variant for I = Kf * R * 512 (Llama-3.1-8B: 28 * 1 * 512; 70B: 28 * 2 * 512).  CTA b owns the 512 consecutive
+// elements of block b: SiLU*mul, sign and the butterflies of stride < 512 stay inside the CTA; the block is published (fp32,
+// in place over the `up` accumulators this CTA alone has read) and, after a grid-wide ticket barrier, every CTA applies the
+// remaining cross-block factor (H_Kf (x) H_R on the block index) to its share of the 512 column positions.  28 SMs pull
+// the 200 KB of inputs instead of one, and the 28-point factor runs 28-wide.
+// Safe to spin: the grid (<= 64 CTAs of 128 threads, 2 KiB smem) is always co-resident, and dependents of a PDL launch are
+// only scheduled after every CTA of this grid has started.  *sync_counter must be 0 before the first launch and is used by
+// one launch at a time (launches of one stream serialise); it advances by gridDim.x per launch.
+constexpr int kSiluBlk = 512, kSiluThreads = kSiluBlk / 4;
+template <int KF, int R>
+__global__ void __launch_bounds__(kSiluThreads)
+silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *__restrict__ wscale, float acc_scale,
+                         const __half *__restrict__ su, int I, float had_scale, float *__restrict__ zero_ptr, int zero_count,
+                         unsigned *sync_counter) {
+    __shared__ __align__(16) float v[kSiluBlk];
+    pdl_wait();
+    pdl_launch_dependents();
+    constexpr int NB = KF * R;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int c = b * kSiluThreads + t;  // this thread's chunk of 4 consecutive elements
+    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
+    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
+    const uint2 wu = reinterpret_cast<const uint2 *>(wscale)[c];
+    const uint2 wg = reinterpret_cast<const uint2 *>(wscale + I)[c];
+    const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    if (zero_ptr) {  // this CTA's slice of the accumulators to clear for later launches
+        const int per = ((zero_count + NB - 1) / NB + 3) & ~3;
+        const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
+        zero_words4(zero_ptr + lo, hi - lo);
+    }
+    const __half hs = __float2half(acc_scale);
+    float w_u[4], w_g[4], s4[4], y[4];
+    unpack4(wu, w_u);
+    unpack4(wg, w_g);
+    unpack4(sv, s4);
+    const float u4[4] = {au.x, au.y, au.z, au.w}, g4[4] = {ag.x, ag.y, ag.z, ag.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float up = scaled_acc(u4[e], w_u[e], hs), g = scaled_acc(g4[e], w_g[e], hs);
+        const __half act = __float2half(g / (1.f + __expf(-g)));
+        y[e] = __half2float(__hmul(act, __float2half(up)));
+        if (su) y[e] *= s4[e];
+    }
+    had_warp128(y);  // strides 1..64
+    reinterpret_cast<float4 *>(v)[t] = make_float4(y[0], y[1], y[2], y[3]);
+    __syncthreads();
+    fwht_pass<2>(v, kSiluBlk, kHadLh0);  // strides 128, 256 across the 4 warps
+    __syncthreads();
+    reinterpret_cast<float4 *>(acc)[c] = reinterpret_cast<const float4 *>(v)[t];  // publish block b
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const unsigned old = atomicAdd(sync_counter, 1u);
+        const unsigned target = old - old % NB + NB;
+        unsigned cur;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(sync_counter) : "memory");
+        } while ((int)(cur - target) < 0);
+        __threadfence();
+    }
+    __syncthreads();
+    // cross-block factor on columns [c_lo, c_hi) of the 512 positions: element (k, r, col) = acc[(k*R + r)*512 + col]
+    const int c_lo = b * kSiluBlk / NB, c_hi = (b + 1) * kSiluBlk / NB;
+    const int col = c_lo + t;
+    if (col < c_hi) {
+        float z[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) z[i] = __ldcg(acc + i * kSiluBlk + col);
+        if (R > 1) {
+#pragma unroll
+            for (int k = 0; k < KF; ++k)
+#pragma unroll
+                for (int st = 1; st < R; st <<= 1)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if ((r & st) == 0) {
+                            const float a0 = z[k * R + r], a1 = z[k * R + (r | st)];
+                            z[k * R + r] = a0 + a1;
+                            z[k * R + (r | st)] = a0 - a1;
+                        }
+        }
+        if (KF == 28) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float u[14], w[14], sju[14], sjw[14];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    u[j] = z[j * R + r];
+                    w[j] = z[(14 + j) * R + r];
+                }
+                jacobsthal14(u, sju);
+                jacobsthal14(w, sjw);
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    z[j * R + r] = (sju[j] + u[j]) + (sjw[j] - w[j]);          // (S+I)u + (S-I)w
+                    z[(14 + j) * R + r] = (sju[j] - u[j]) - (sjw[j] + w[j]);   // (S-I)u - (S+I)w
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) x_out[i * kSiluBlk + col] = __float2half(z[i] * had_scale);
+    }
+}
+
 // One CTA (256 threads) per query head.  acc_qkv: fp32 [q (H*D) | k (Hkv*D) | v (Hkv*D)] raw GEMV sums; wscale same layout.
 // RoPE (HF rotate_half convention, model/llama.py apply_rotary_pos_emb) with inv_freq table (D/2 floats, llama3 scaling
 // already applied by the host).  KV cache: fp16 [max_seq][Hkv][D] per layer.  pos read from device memory.
@@ -544,6 +648,28 @@ extern "C" int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *ws
                        (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, m, Kf, had_scale, zero_ptr,
                        zero_count));
     return check_launch("silu_mul_had");
+}
+
+extern "C" int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wscale_f16, float acc_scale, const void *su_f16,
+                                    int I, float had_scale, float *zero_ptr, int zero_count, unsigned *sync_counter,
+                                    void *stream) {
+    QP_CHECK_ARG(x_out_f16 && acc && wscale_f16 && sync_counter, "NULL pointer argument");
+    int m, Kf;
+    int rc = had_dims(I, m, Kf);
+    if (rc != QP_OK) return rc;
+    QP_CHECK_ARG(m % kSiluBlk == 0, "I = %d: the multi-CTA kernel needs a power-of-two factor >= 512 (use qp_silu_mul_had)", I);
+    const int R = m / kSiluBlk;
+    void (*kern)(__half *, float *, const __half *, float, const __half *, int, float, float *, int, unsigned *) = nullptr;
+    if (Kf == 28 && R == 1) kern = silu_mul_had_grid_kernel<28, 1>;
+    else if (Kf == 28 && R == 2) kern = silu_mul_had_grid_kernel<28, 2>;
+    else if (Kf == 1 && R == 8) kern = silu_mul_had_grid_kernel<1, 8>;
+    else if (Kf == 1 && R == 16) kern = silu_mul_had_grid_kernel<1, 16>;
+    else if (Kf == 1 && R == 32) kern = silu_mul_had_grid_kernel<1, 32>;
+    QP_CHECK_ARG(kern != nullptr, "I = %d = %d * %d * 512 is not instantiated for the multi-CTA kernel (use qp_silu_mul_had)", I, Kf, R);
+    QP_CUDA(launch_pdl(kern, dim3(Kf * R), dim3(kSiluThreads), 0, (cudaStream_t)stream, (__half *)x_out_f16, acc,
+                       (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, had_scale, zero_ptr, zero_count,
+                       sync_counter));
+    return check_launch("silu_mul_had_grid");
 }
 
 extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
     "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
+    "qp_silu_mul_had_grid": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp],
     "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "qp_gemv_f16": [_vp, _vp, _vp, _i, _i, _vp],
     "qp_argmax": [_vp, _vp, _i, _vp, _vp],

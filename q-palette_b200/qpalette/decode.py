@@ -133,6 +133,14 @@ class _Proj:
                                       self.K, self.bits, self.vec, stream))
 
 
+def silu_grid_supported(I):
+    """shapes the multi-CTA SiLU*mul + Hadamard kernel is instantiated for: I = Kf * R * 512 (csrc/decode_kernels.cu)"""
+    for kf, rs in ((28, (1, 2)), (1, (8, 16, 32))):
+        if I % (kf * 512) == 0 and I // (kf * 512) in rs:
+            return True
+    return False
+
+
 class DecodeRunner:
     def __init__(self, shape=LLAMA31_8B, qdict=None, merge_info=None, max_seq=512, device="cuda", seed=0, rank=0,
                  world=1, process_group=None, num_layers=None, random_scales=True, fused=True):
@@ -232,6 +240,8 @@ class DecodeRunner:
         self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.history = torch.zeros(max_seq, dtype=torch.int32, device=self.dev)
         self.scratch = torch.zeros(4096, dtype=torch.uint8, device=self.dev)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=self.dev)  # ticket of the multi-CTA SiLU*mul/Hadamard kernel
+        self.silu_grid = silu_grid_supported(self.I)
         self.graph = None
         self.lm_head_bytes = self.lm_head.numel() * 2
         self.launches_per_step = 0
@@ -292,7 +302,11 @@ class DecodeRunner:
             prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"])
             run_group(ly["ug"], self.acc_ug, prod, self.x_h)
             hc, ho = ho, hc
-            check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
+            if self.silu_grid:
+                check(L.qp_silu_mul_had_grid(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0,
+                                             p(self.sync), st))
+            else:
+                check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
             ly["down"].launch(p(self.acc_dn), p(self.x_i), st)
             prev = ly
         check(L.qp_fused_norm_had(p(self.xf), p(hc), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),

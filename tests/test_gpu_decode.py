@@ -224,3 +224,45 @@ def test_decode_step_matches_restatement(variant, fused):
     r.capture()
     assert r.generate(4, token=7) == eager
     assert r.launches_per_step > 0
+
+
+@pytest.mark.parametrize("I", [28 * 512, 28 * 1024, 4096, 8192])
+def test_silu_mul_had_grid(I):
+    """multi-CTA SiLU*mul + Hadamard (grid ticket barrier) vs the float64 restatement and vs the single-CTA kernel;
+    launched repeatedly on one counter, with the accumulator-clearing duty"""
+    import math
+    from qpalette._cabi import lib, check
+    rng = np.random.default_rng(I)
+    dev = "cuda"
+    acc = (rng.standard_normal(2 * I) * 3).astype(np.float32)
+    ws = (rng.uniform(0.5, 1.5, 2 * I) / 64).astype(np.float16)
+    su = rng.choice([-1.0, 1.0], I).astype(np.float16)
+    S, had_scale = 64.0, 1.0 / (math.sqrt(I) * 64.0)
+    # float64 restatement with the reference's fp16 rounding points (incoherent_linear.py:324-338)
+    h = lambda a: np.asarray(a, np.float16)
+    ug = h(h(h(acc) * ws) * np.float16(S)).astype(np.float64)
+    up, gate = ug[:I], ug[I:]
+    act = h(gate / (1.0 + np.exp(-gate))).astype(np.float64)
+    y = h(act * up).astype(np.float64) * su.astype(np.float64)
+    ref = O.hadamard_ref(y[None, :])[0] * math.sqrt(I) * had_scale
+
+    t = lambda a: torch.from_numpy(a).to(dev)
+    ws_d, su_d = t(ws), t(su)
+    sync = torch.zeros(4, dtype=torch.int32, device=dev)
+    zero = torch.ones(1000, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for it in range(3):
+        acc_d, x_d = t(acc.copy()), torch.empty(I, dtype=torch.float16, device=dev)
+        check(lib().qp_silu_mul_had_grid(x_d.data_ptr(), acc_d.data_ptr(), ws_d.data_ptr(), S, su_d.data_ptr(), I, had_scale,
+                                         zero.data_ptr(), zero.numel(), sync.data_ptr(), st))
+        outs.append(x_d.float().cpu().numpy())
+    torch.cuda.synchronize()
+    assert int(sync[0].item()) == 3 * (I // 512)
+    assert float(zero.abs().sum().item()) == 0.0
+    x1 = torch.empty(I, dtype=torch.float16, device=dev)
+    check(lib().qp_silu_mul_had(x1.data_ptr(), t(acc).data_ptr(), ws_d.data_ptr(), S, su_d.data_ptr(), I, had_scale, None, 0, st))
+    single = x1.float().cpu().numpy()
+    for o in outs:
+        assert np.linalg.norm(o - ref) / np.linalg.norm(ref) <= 1e-3
+        assert np.linalg.norm(o - single) / np.linalg.norm(single) <= 1e-3
