@@ -182,7 +182,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--parallel", default="replicas", choices=["tp", "replicas"],
                     help="N > 1: independent bs=1 decode streams per GPU (default, weak scaling) or row-sharded tensor parallel")
-    ap.add_argument("--workload", default="8b", choices=["8b", "70b"])
+    ap.add_argument("--workload", default="8b", choices=["8b", "70b", "figure1d", "figure1c"],
+                    help="8b / 70b: uniform TCQ-3.25 (headline = 8b); figure1d / figure1c: the reference's shipped mixed-scheme "
+                         "MSQ qdict + merge_info for Llama-3.1-8B (configs/*.json, BASELINE.json configs[2])")
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (invalid as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -206,10 +208,20 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     tp = world if args.parallel == "tp" else 1
 
-    shape = LLAMA31_8B if args.workload == "8b" else LLAMA31_70B
+    shape = LLAMA31_70B if args.workload == "70b" else LLAMA31_8B
     W = max(args.warmup, 3)
     max_seq = max(64, W + args.steps * 2 + 16)
-    runner = DecodeRunner(shape, uniform_qdict(shape, QUANTIZER), [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers,
+    if args.workload in ("figure1d", "figure1c"):
+        cfg = json.load(open(os.path.join(ROOT, "configs", args.workload + ".json")))
+        qdict = {k: tuple(v) for k, v in cfg["qdict"].items()}
+        merge_info = cfg["merge_info"]
+        wl_name = f"Llama-3.1-8B bs=1 decode, mixed-scheme MSQ qdict {cfg['source']} (TCQ/tcomb/VQ/SQ mix, per-layer merges)"
+        q_name = "mixed"
+    else:
+        qdict, merge_info = uniform_qdict(shape, QUANTIZER), [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers
+        wl_name = WORKLOAD if args.workload == "8b" else WORKLOAD.replace("8B", "70B-shaped")
+        q_name = QUANTIZER
+    runner = DecodeRunner(shape, qdict, merge_info,
                           max_seq=max_seq, seed=0, rank=rank if tp > 1 else 0, world=tp, process_group=pg if tp > 1 else None,
                           num_layers=args.layers)
     runner.capture()
@@ -329,9 +341,10 @@ def main():
             "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.parallel == "tp" else "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.workload == "8b" else WORKLOAD.replace("8B", "70B-shaped"),
-                       "quantizer": QUANTIZER, "parallelism": f"{args.parallel}{world}", "layers": runner.L,
-                       "l2_policy": "inputs larger than L2: 3.9 GB of weights streamed per step, no reuse between steps",
+            "config": {"workload": wl_name,
+                       "quantizer": q_name, "parallelism": f"{args.parallel}{world}", "layers": runner.L,
+                       "l2_policy": f"inputs larger than L2: {runner.bytes_per_token() / 1e9:.1f} GB of weights streamed per step, "
+                                    "no reuse between steps",
                        "max_seq": max_seq},
             "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_detail": detail,
