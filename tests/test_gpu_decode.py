@@ -191,12 +191,14 @@ def _ref_layer_step(r, x_in_h, pos, caches):
 
 
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged"])
+@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged", "uniform_merged_grid_silu"])
 def test_decode_step_matches_restatement(variant, fused):
     from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
-    shape = LlamaShape(hidden_size=512, intermediate_size=28 * 128, num_hidden_layers=2, num_attention_heads=8,
+    # intermediate 4096 = 8 * 512 takes the multi-CTA SiLU*mul/Hadamard kernel in the fused list, 28 * 128 the single-CTA one
+    inter = 4096 if variant == "uniform_merged_grid_silu" else 28 * 128
+    shape = LlamaShape(hidden_size=512, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=8,
                        num_key_value_heads=2, vocab_size=1024)
-    if variant == "uniform_merged":
+    if variant.startswith("uniform_merged"):
         qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 2
     else:
         qd = uniform_qdict(shape, "tcq_8_none_0.9")
@@ -266,3 +268,28 @@ def test_silu_mul_had_grid(I):
     for o in outs:
         assert np.linalg.norm(o - ref) / np.linalg.norm(ref) <= 1e-3
         assert np.linalg.norm(o - single) / np.linalg.norm(single) <= 1e-3
+
+
+def test_figure1d_layers_fused_vs_unfused():
+    """first layers of the reference's shipped mixed-scheme config (configs/figure1d.json) at the real Llama-3.1-8B
+    shapes: the fused and the unfused launch lists (independent glue kernels) produce the same logits and tokens"""
+    import json, os
+    from qpalette.decode import DecodeRunner, LLAMA31_8B
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = json.load(open(os.path.join(root, "configs", "figure1d.json")))
+    qd = {k: tuple(v) for k, v in cfg["qdict"].items()}
+    logits = []
+    for fused in (True, False):
+        r = DecodeRunner(LLAMA31_8B, qd, cfg["merge_info"], max_seq=16, seed=11, num_layers=3, fused=fused)
+        r.reset(9)
+        outs = []
+        for _ in range(2):
+            r.step()
+            torch.cuda.synchronize()
+            outs.append(r.logits.float().cpu().numpy().copy())
+        logits.append(outs)
+        del r
+        torch.cuda.empty_cache()
+    for a, b in zip(*logits):
+        assert np.isfinite(a).all() and np.isfinite(b).all()
+        assert rel_l2(a, b) <= 2e-2
