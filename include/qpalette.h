@@ -121,6 +121,30 @@ int qp_scale_epilogue(void *out_f16, const float *acc, const void *wscale_f16, i
 int qp_fused_norm_had(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
                       float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
                       int do_had, float *zero_ptr, int zero_count, void *stream);
+/* Row-sharded layers (one process per GPU): the buffer a layer boundary gathers (attention output, o / down accumulators,
+ * SiLU*mul activations -- SURVEY 8e) lives at `offset` of an "exchange region" every rank has allocated with
+ * qp_peer_alloc and mapped from every peer (qp_peer_export -> any host transport -> qp_peer_import).  Rank r has produced
+ * bytes [r*slice_bytes, (r+1)*slice_bytes) of it; qp_fused_norm_had_xchg completes it in place by pushing that slice to all
+ * peers over NVLink and waiting for theirs (flags[site*nranks + source] inside each rank's region, epoch[site] local),
+ * then runs qp_fused_norm_had on it: all-gather + consumer in one kernel, no NCCL call.  A site is one (layer, gather
+ * point); every rank must run the same sequence of sites.  zero_ptr is cleared BEFORE the flags are published. */
+typedef struct qp_xchg {
+    void *const *peer_base;     /* device array [nranks] of region base pointers (entry `rank` = the local region) */
+    unsigned *const *peer_flags;/* device array [nranks] of flag-array pointers (inside the regions) */
+    unsigned *epoch;            /* local device array [nsites], zero-initialised */
+    long long offset;           /* of the gathered buffer inside the region, bytes, multiple of 16 */
+    int slice_bytes;            /* per rank, multiple of 16 */
+    int rank, nranks, site;
+} qp_xchg;
+int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
+                           float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
+                           int do_had, float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
+int qp_peer_alloc(void **ptr, size_t bytes);             /* cudaMalloc + clear */
+int qp_peer_free(void *ptr);
+int qp_peer_export(void *ptr, void *handle64);           /* 64-byte CUDA IPC handle of a qp_peer_alloc region */
+int qp_peer_import(const void *handle64, void **ptr);    /* map a peer's region (enables peer access) */
+int qp_peer_close(void *ptr);
+
 /* acc = [up | gate] (2*I fp32): x_out = fp16(Hadamard(silu(gate)*up * su) * had_scale)   (IncoherentMLP.compute_ug tail
  * + compute_dp head, lib/linear/incoherent_linear.py:324-338) */
 int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *wscale_f16, float acc_scale, const void *su_f16,

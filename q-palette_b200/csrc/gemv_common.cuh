@@ -125,6 +125,10 @@ struct PackSegment {
 #ifndef QP_GEMV_DEPTH
 #define QP_GEMV_DEPTH 3
 #endif
+#ifndef QP_GEMV_CTAS
+#define QP_GEMV_CTAS 1
+#endif
+constexpr int kGemvCtasPerSM = QP_GEMV_CTAS;    // experiments: 2 CTAs of 384 threads per SM (needs a <= 64 KiB codebook)
 constexpr int kGemvThreads = QP_GEMV_THREADS;   // one CTA per SM (the lane-replicated codebook takes 128 KiB)
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kGemvDepth = QP_GEMV_DEPTH;       // super-tiles prefetched ahead per warp (register staged)

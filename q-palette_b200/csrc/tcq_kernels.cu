@@ -44,7 +44,10 @@ constexpr int kTcqWarps = kGemvWarps;
 template <int S>
 struct TcqTable {
     static_assert(S >= 9 && S <= 11, "tlut_bits must be 9, 10 or 11");
-    static constexpr bool kFold = (S == 9);
+#ifndef QP_TCQ_FOLD
+#define QP_TCQ_FOLD 1
+#endif
+    static constexpr bool kFold = (S == 9) && QP_TCQ_FOLD;
     static constexpr int kStrideLog2 = (S == 11) ? 6 : 7;
     static constexpr int kEntryBits = S + (kFold ? 1 : 0);
     static constexpr int kEntries = 1 << kEntryBits;
@@ -128,7 +131,7 @@ using TcqSegment = PackSegment;
 
 // ---- GEMV -----------------------------------------------------------------------------------------------------------
 template <int KVA, int KVB, int S>
-__global__ void __launch_bounds__(kTcqThreads, 1)
+__global__ void __launch_bounds__(kTcqThreads, kGemvCtasPerSM)
 tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
                 const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, XProd prod) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -240,7 +243,7 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
         configured = true;
     }
-    const int nctas = sm_count();
+    const int nctas = sm_count() * kGemvCtasPerSM;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
                        make_split((long)L.a.strips * L.a.ksuper, nctas), make_split((long)L.b.strips * L.b.ksuper, nctas),
                        out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));

@@ -33,6 +33,12 @@ SIGNATURES = {
     "qp_hadamard": [_vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
+    "qp_fused_norm_had_xchg": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp, _vp],
+    "qp_peer_alloc": [_vp, ctypes.c_size_t],
+    "qp_peer_free": [_vp],
+    "qp_peer_export": [_vp, _vp],
+    "qp_peer_import": [_vp, _vp],
+    "qp_peer_close": [_vp],
     "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_grid": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp],
     "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
@@ -52,6 +58,12 @@ class XProd(ctypes.Structure):
     _fields_ = [("src_f16", _vp), ("h_out_f16", _vp), ("acc", _vp), ("wscale_f16", _vp), ("acc_scale", _f),
                 ("norm_w_f16", _vp), ("eps", _f), ("su_f16", _vp), ("had_scale", _f), ("x_out_f16", _vp),
                 ("zero1", _vp), ("zero1_count", _i), ("zero2", _vp), ("zero2_count", _i)]
+
+
+class Xchg(ctypes.Structure):
+    """mirror of `qp_xchg` (include/qpalette.h)"""
+    _fields_ = [("peer_base", _vp), ("peer_flags", _vp), ("epoch", _vp), ("offset", ctypes.c_longlong),
+                ("slice_bytes", _i), ("rank", _i), ("nranks", _i), ("site", _i)]
 
 
 class QPaletteError(RuntimeError):

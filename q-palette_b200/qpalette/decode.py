@@ -14,6 +14,7 @@ Row sharding (tensor parallel over output rows): with world_size >
 [rank, rank+1) * M/world of each projection (a zero-copy slice of the strip-major packed buffers) and the partial outputs
 are all-gathered with NCCL at the four layer boundaries.
 """
+import ctypes
 import math
 from dataclasses import dataclass, field
 
@@ -143,8 +144,12 @@ def silu_grid_supported(I):
 
 class DecodeRunner:
     def __init__(self, shape=LLAMA31_8B, qdict=None, merge_info=None, max_seq=512, device="cuda", seed=0, rank=0,
-                 world=1, process_group=None, num_layers=None, random_scales=True, fused=True):
+                 world=1, process_group=None, num_layers=None, random_scales=True, fused=True, p2p=True):
+        """world > 1: rows of every projection are sharded over the ranks of `process_group`.  p2p=True gathers
+        at the four layer boundaries by NVLink peer stores fused into the consumer kernel (qp_fused_norm_had_xchg);
+        p2p=False uses ncclAllGather (the baseline)."""
         self.shape, self.dev, self.rank, self.world, self.pg = shape, torch.device(device), rank, world, process_group
+        self.p2p = p2p and world > 1
         self.L = num_layers or shape.num_hidden_layers
         self.max_seq = max_seq
         self.fused = fused and world == 1   # GEMV-prologue fusion of the glue (single-GPU path)
@@ -226,14 +231,25 @@ class DecodeRunner:
         self.h2 = torch.zeros(H, **f16)          # ping-pong partner of h for the fused prologues
         self.x_h = torch.zeros(H, **f16)
         self.x_i = torch.zeros(I, **f16)
-        self.attn = torch.zeros(H, **f16)       # full attention output (all-gathered when sharded)
+        self.region = None
+        if self.p2p:
+            # the four gathered buffers live in a region every peer maps; site = 4 * layer + {attn, o, act, down}
+            from .peer import PeerRegion
+            self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4)], 4 * self.L + 4,
+                                     rank, world, process_group, self.dev)
+            self.attn = self.region.tensor("attn", torch.float16)
+            self.acc_o = self.region.tensor("acc_o", torch.float32)
+            self.act = self.region.tensor("act", torch.float16)
+            self.acc_dn = self.region.tensor("acc_dn", torch.float32)
+        else:
+            self.attn = torch.zeros(H, **f16)       # full attention output (all-gathered when sharded)
+            self.acc_o = torch.zeros(H, **z32)       # full width; each rank fills its slice, then all-gather
+            self.acc_dn = torch.zeros(H, **z32)
+            self.act = torch.zeros(I, **f16)
         self.attn_loc = torch.zeros(Hq, **f16)
         self.acc_qkv = torch.zeros(Hq + 2 * Hk, **z32)
-        self.acc_o = torch.zeros(H, **z32)       # full width; each rank fills its slice, then all-gather
         self.acc_ug = torch.zeros(2 * Il, **z32)
-        self.acc_dn = torch.zeros(H, **z32)
         self.act_loc = torch.zeros(Il, **f16)    # sharded silu(gate)*up
-        self.act = torch.zeros(I, **f16)
         self.xf = torch.zeros(H, **f16)
         self.logits = torch.zeros(V, **z32)
         self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -328,47 +344,61 @@ class DecodeRunner:
         s_h, s_i, S = 1.0 / (math.sqrt(H) * 64.0), 1.0 / (math.sqrt(I) * 64.0), 64.0
         Hq, Hk, Il, Ho = H // world, self.kvd // world, I // world, H // world
         check(L.qp_embed(p(self.h), p(self.embed), p(self.token), H, st))
+        p2p, gather = self.p2p, world > 1 and not self.p2p
+        keep = self._xchg_keep = []
+
+        def norm_had(site, name, *args):
+            """qp_fused_norm_had, preceded (p2p) by the in-kernel NVLink all-gather of region buffer `name`"""
+            if p2p and name is not None:
+                xc = self.region.xchg(name, site)
+                keep.append(xc)
+                check(L.qp_fused_norm_had_xchg(*args, ctypes.byref(xc), st))
+            else:
+                check(L.qp_fused_norm_had(*args, st))
+
         prev = None
-        for ly in self.layers:
+        for li, ly in enumerate(self.layers):
             # residual from the previous layer's down_proj, input_layernorm, SU, Hadamard -> x_h ; zero acc_qkv
             if prev is None:
-                check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 0, None, None, 0.0, p(ly["norm1"]), sh.rms_norm_eps,
-                                          p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv), self.acc_qkv.numel(), st))
+                norm_had(0, None, p(self.x_h), p(self.h), 0, None, None, 0.0, p(ly["norm1"]), sh.rms_norm_eps,
+                         p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv), self.acc_qkv.numel())
             else:
-                check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(ly["norm1"]),
-                                          sh.rms_norm_eps, p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv),
-                                          self.acc_qkv.numel(), st))
+                norm_had(4 * (li - 1) + 3, "acc_dn", p(self.x_h), p(self.h), 1, p(self.acc_dn), p(prev["W_dp_full"]), S,
+                         p(ly["norm1"]), sh.rms_norm_eps, p(ly["SU_qkv"]), H, s_h, 1, p(self.acc_qkv), self.acc_qkv.numel())
             for proj, off in ly["qkv"]:
                 proj.launch(p(self.acc_qkv) + 4 * off, p(self.x_h), st)
-            attn_dst = self.attn if world == 1 else self.attn_loc
-            check(L.qp_rope_attention(p(attn_dst), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
+            # sharded: every rank writes its heads into its slice of the full-width buffer
+            attn_dst = p(self.attn) + 2 * rank * Hq if p2p else (p(self.attn) if world == 1 else p(self.attn_loc))
+            check(L.qp_rope_attention(attn_dst, p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
                                       sh.num_key_value_heads // world, sh.head_dim, self.max_seq, None, 0, st))
-            if world > 1:
+            if gather:
                 torch.distributed.all_gather_into_tensor(self.attn, self.attn_loc, group=self.pg)
-            check(L.qp_fused_norm_had(p(self.x_h), p(self.attn), 0, None, None, 0.0, None, 0.0, p(ly["SU_o"]), H, s_h, 1,
-                                      p(self.acc_o), self.acc_o.numel(), st))
+            norm_had(4 * li + 0, "attn", p(self.x_h), p(self.attn), 0, None, None, 0.0, None, 0.0, p(ly["SU_o"]), H, s_h, 1,
+                     p(self.acc_o), self.acc_o.numel())
             ly["o"].launch(p(self.acc_o) + 4 * rank * Ho, p(self.x_h), st)
-            if world > 1:
+            if gather:
                 torch.distributed.all_gather_into_tensor(self.acc_o, self.acc_o[rank * Ho:(rank + 1) * Ho], group=self.pg)
-            check(L.qp_fused_norm_had(p(self.x_h), p(self.h), 1, p(self.acc_o), p(ly["W_o_full"]), S, p(ly["norm2"]),
-                                      sh.rms_norm_eps, p(ly["SU_ug"]), H, s_h, 1, p(self.acc_ug), self.acc_ug.numel(), st))
+            norm_had(4 * li + 1, "acc_o", p(self.x_h), p(self.h), 1, p(self.acc_o), p(ly["W_o_full"]), S, p(ly["norm2"]),
+                     sh.rms_norm_eps, p(ly["SU_ug"]), H, s_h, 1, p(self.acc_ug), self.acc_ug.numel())
             for proj, off in ly["ug"]:
                 proj.launch(p(self.acc_ug) + 4 * off, p(self.x_h), st)
             if world == 1:
                 check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i,
                                         p(self.acc_dn), self.acc_dn.numel(), st))
             else:
-                check(L.qp_scale_epilogue(p(self.act_loc), p(self.acc_ug), p(ly["W_ug"]), 1, 2 * Il, S, _cabi.EPI_SILU_MUL, st))
-                torch.distributed.all_gather_into_tensor(self.act, self.act_loc, group=self.pg)
-                check(L.qp_fused_norm_had(p(self.x_i), p(self.act), 0, None, None, 0.0, None, 0.0, p(ly["SU_dp"]), I, s_i, 1,
-                                          p(self.acc_dn), self.acc_dn.numel(), st))
+                act_dst = p(self.act) + 2 * rank * Il if p2p else p(self.act_loc)
+                check(L.qp_scale_epilogue(act_dst, p(self.acc_ug), p(ly["W_ug"]), 1, 2 * Il, S, _cabi.EPI_SILU_MUL, st))
+                if gather:
+                    torch.distributed.all_gather_into_tensor(self.act, self.act_loc, group=self.pg)
+                norm_had(4 * li + 2, "act", p(self.x_i), p(self.act), 0, None, None, 0.0, None, 0.0, p(ly["SU_dp"]), I, s_i, 1,
+                         p(self.acc_dn), self.acc_dn.numel())
             ly["down"].launch(p(self.acc_dn) + 4 * rank * Ho, p(self.x_i), st)
-            if world > 1:
+            if gather:
                 torch.distributed.all_gather_into_tensor(self.acc_dn, self.acc_dn[rank * Ho:(rank + 1) * Ho], group=self.pg)
             prev = ly
-        check(L.qp_fused_norm_had(p(self.xf), p(self.h), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
-                                  sh.rms_norm_eps, None, H, 1.0, 0, None, 0, st))
+        norm_had(4 * (len(self.layers) - 1) + 3, "acc_dn" if world > 1 else None, p(self.xf), p(self.h), 1, p(self.acc_dn),
+                 p(prev["W_dp_full"]), S, p(self.final_norm), sh.rms_norm_eps, None, H, 1.0, 0, None, 0)
         check(L.qp_gemv_f16(p(self.logits), p(self.lm_head), p(self.xf), sh.vocab_size, H, st))
         check(L.qp_argmax(p(self.token), p(self.logits), sh.vocab_size, p(self.scratch), st))
         check(L.qp_step_advance(p(self.pos), p(self.history), p(self.token), self.max_seq, st))
