@@ -107,6 +107,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (spin > (1u << 26)) __trap();  // never hang the GPU on a protocol bug
+#ifdef QP_TC_BACKOFF
+        if (!ok) __nanosleep(QP_TC_BACKOFF);  // leave the issue slots to the decode warps while waiting
+#endif
     }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

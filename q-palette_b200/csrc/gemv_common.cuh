@@ -5,6 +5,12 @@
 
 namespace qp {
 
+// start of the dynamic shared memory: the GEMV / dequantise kernels keep their lane-replicated codebook there, so a lookup
+// address is (uniform base) + ((slot offset) | (lane column)) -- one LOP3 and an LDS with a uniform-register base, no
+// per-lookup pointer add.  `tab_lane` below is that lane column: (lane & lane_mask) * 4.
+extern __shared__ __align__(16) uint8_t qp_dyn_smem[];
+
+
 // per-lane fetch of one super-tile payload (2*E bytes, lane-contiguous) with the widest load the alignment allows
 template <int E>
 __device__ __forceinline__ void pack_load_raw(uint32_t (&raw)[TcqGeom<E>::kRawWords], const uint32_t *p) {
@@ -234,7 +240,7 @@ __device__ __forceinline__ void gemv_prefetch(const PackSegment seg, const WarpR
 // one super-tile: consume slot `raw` (decode -> 4 mma), refill it with the super-tile kGemvDepth steps ahead
 template <class Dec, bool kRefillAlways>
 __device__ __forceinline__ void gemv_step(uint32_t (&raw)[TcqGeom<Dec::kE>::kRawWords], const uint32_t *pnext,
-                                          bool refill, int bitoff, int lane, const uint8_t *tab_lane,
+                                          bool refill, int bitoff, int lane, uint32_t tab_lane,
                                           const uint8_t *xs_lane, bool xvalid, float (&acc)[2][4]) {
     constexpr int E = Dec::kE;
     using G = TcqGeom<E>;
@@ -259,7 +265,7 @@ __device__ __forceinline__ void gemv_step(uint32_t (&raw)[TcqGeom<Dec::kE>::kRaw
 // latency hides behind this part's tail).
 template <class Dec, class Between>
 __device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *__restrict__ out, int M, int bs,
-                                                 const uint8_t *xs, const uint8_t *tab_lane, const WarpRun run,
+                                                 const uint8_t *xs, uint32_t tab_lane, const WarpRun run,
                                                  uint32_t (&raw)[kGemvDepth][TcqGeom<Dec::kE>::kRawWords],
                                                  Between between) {
     constexpr int E = Dec::kE;
@@ -323,7 +329,7 @@ __device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *_
 
 template <class Dec>
 __device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *__restrict__ out, int M, int bs,
-                                                 const uint8_t *xs, const uint8_t *tab_lane, const WarpRun run,
+                                                 const uint8_t *xs, uint32_t tab_lane, const WarpRun run,
                                                  uint32_t (&raw)[kGemvDepth][TcqGeom<Dec::kE>::kRawWords]) {
     gemv_run_segment<Dec>(seg, out, M, bs, xs, tab_lane, run, raw, [] {});
 }
@@ -331,7 +337,7 @@ __device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *_
 // decode the warp's share of one part and write fp16 W (M, K) row-major
 template <class Dec>
 __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __half *__restrict__ W, int K,
-                                                    const uint8_t *tab_lane, RunSplit split, int gwarp) {
+                                                    uint32_t tab_lane, RunSplit split, int gwarp) {
     constexpr int E = Dec::kE;
     using G = TcqGeom<E>;
     const int lane = threadIdx.x & 31;

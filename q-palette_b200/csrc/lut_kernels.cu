@@ -53,24 +53,24 @@ struct LutDecoder {
     using T = LutTable<E, SPLIT>;
 
     template <int TI, int J>
-    __device__ static __forceinline__ uint32_t one(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab) {
+    __device__ static __forceinline__ uint32_t one(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab) {
         if constexpr (!SPLIT) {
-            return *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, J, T::kSL>(P));
+            return *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (lut_pair_offset<E, TI, J, T::kSL>(P) | tab));
         } else {
-            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tab + lut_single_offset<E, TI, J, 0, T::kSL>(P));
-            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tab + lut_single_offset<E, TI, J, 1, T::kSL>(P));
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (lut_single_offset<E, TI, J, 0, T::kSL>(P) | tab));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (lut_single_offset<E, TI, J, 1, T::kSL>(P) | tab));
             return __byte_perm(w0, w1, 0x5410);
         }
     }
     template <int TI>
-    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab, uint32_t (&f)[4]) {
+    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], uint32_t tab, uint32_t (&f)[4]) {
         f[0] = one<TI, 0>(P, tab);
         f[1] = one<TI, 1>(P, tab);
         f[2] = one<TI, 2>(P, tab);
         f[3] = one<TI, 3>(P, tab);
     }
     __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<E>::kWords], int lane,
-                                                  const uint8_t *tab_addr_lane, uint32_t (&frag)[4][4]) {
+                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
         (void)lane;
         tile<0>(P, tab_addr_lane, frag[0]);
         tile<1>(P, tab_addr_lane, frag[1]);
@@ -103,7 +103,7 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
     __syncthreads();
     pdl_launch_dependents();
-    const uint8_t *tab_addr_lane = smem + ((lane & T::kLaneMask) << 2);
+    const uint32_t tab_addr_lane = (lane & T::kLaneMask) << 2;  // the table starts the dynamic shared memory
     gemv_run_segment<LutDecoder<E, SPLIT>>(seg, out, M, bs, reinterpret_cast<const uint8_t *>(xs), tab_addr_lane, run, raw);
 }
 
@@ -121,7 +121,7 @@ lut_dequant_kernel(PackSegment seg, RunSplit split, __half *__restrict__ W, cons
     __syncthreads();
     lut_build_table<E, SPLIT>(tab, lc, r_single);
     __syncthreads();
-    const uint8_t *tab_addr_lane = smem + ((lane & T::kLaneMask) << 2);
+    const uint32_t tab_addr_lane = (lane & T::kLaneMask) << 2;  // the table starts the dynamic shared memory
     dequant_run_segment<LutDecoder<E, SPLIT>>(seg, W, K, tab_addr_lane, split, gwarp);
 }
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *_
 }
 
 template <int S>
-__device__ __forceinline__ uint32_t tcq_lookup(const uint8_t *tab_lane, uint32_t u) {
+__device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_lane, uint32_t u) {
     using T = TcqTable<S>;
     // hash t = u*(u+1) pre-shifted by kShift with two multiply-adds (fma pipe) instead of multiply + shift/add (alu pipe,
     // which the extraction shifts and the mask already saturate): t << k = u * ((u << k) + (1 << k))
@@ -96,7 +96,7 @@ __device__ __forceinline__ uint32_t tcq_lookup(const uint8_t *tab_lane, uint32_t
 #endif
     // slot offset = hash bits [15-S, 15-S+kEntryBits) moved to [kStrideLog2, ...); tab_lane already carries the lane's
     // 4-byte column, so the address is base + offset with no further arithmetic
-    uint32_t w = *reinterpret_cast<const uint32_t *>(tab_lane + (ts & T::kMask));
+    uint32_t w = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + ((ts & T::kMask) | tab_lane));
     if (!T::kFold) w ^= ((ts >> T::kShift) & 0x8000u);
     return w;
 }
@@ -106,7 +106,7 @@ template <int KV, int S>
 struct TcqDecoder {
     static constexpr int kE = KV;
     __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<KV>::kWords], int lane,
-                                                  const uint8_t *tab_addr_lane, uint32_t (&frag)[4][4]) {
+                                                  uint32_t tab_addr_lane, uint32_t (&frag)[4][4]) {
         using G = TcqGeom<KV>;
         uint32_t send[4] = {tcq_send<KV, 0>(P), tcq_send<KV, 1>(P), tcq_send<KV, 2>(P), tcq_send<KV, 3>(P)};
         uint32_t n1[4], n2[4];
@@ -159,7 +159,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     QP_PHASE(4);
     pdl_launch_dependents();
 
-    const uint8_t *tab_addr_lane = smem + ((lane & TcqTable<S>::kLaneMask) << 2);
+    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
     const uint8_t *xs_addr = reinterpret_cast<const uint8_t *>(xs);
     if constexpr (KVB == 0) {
         gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA);
@@ -191,7 +191,7 @@ tcq_dequant_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit s
     const int gwarp = blockIdx.x * kTcqWarps + warp_in_cta();
     tcq_build_table<S>(tab, tlut);
     __syncthreads();
-    const uint8_t *tab_addr_lane = smem + ((lane & TcqTable<S>::kLaneMask) << 2);
+    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
     dequant_run_segment<TcqDecoder<KVA, S>>(segA, W, K, tab_addr_lane, splitA, gwarp);
     if constexpr (KVB != 0) dequant_run_segment<TcqDecoder<KVB, S>>(segB, W, K, tab_addr_lane, splitB, gwarp);
 }
