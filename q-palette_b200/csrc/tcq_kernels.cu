@@ -57,30 +57,47 @@ struct TcqTable {
     static constexpr uint32_t kLaneMask = (1u << (kStrideLog2 - 2)) - 1u;
 };
 
-// lane-replicated codebook straight from global memory: every thread first issues all its tlut loads (one L2 round
-// trip), then stores.  A warp store covers 4 consecutive 128-byte slots (8 lanes x 16 bytes each).
+// lane-replicated codebook straight from global memory, in two halves so that the kernels can put other work between
+// them: tcq_table_load issues all of a thread's tlut loads (one L2 round trip), tcq_table_store writes the copies.
+// A warp store covers 4 consecutive 128-byte slots (8 lanes x 16 bytes each).
 template <int S>
-__device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *__restrict__ tlut) {
+struct TcqTableRegs {
+    static constexpr int kRows = TcqTable<S>::kBytes / 128;  // 128-byte rows of the table
+    static constexpr int kIter = (kRows + kGemvWarps * 4 - 1) / (kGemvWarps * 4);
+    uint32_t v[kIter];
+};
+
+template <int S>
+__device__ __forceinline__ void tcq_table_load(TcqTableRegs<S> &t, const uint32_t *__restrict__ tlut) {
     using T = TcqTable<S>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-    constexpr int kRows = T::kBytes / 128;              // 128-byte rows of the table
-    constexpr int kIter = (kRows + kGemvWarps * 4 - 1) / (kGemvWarps * 4);
-    uint32_t v[kIter];
 #pragma unroll
-    for (int it = 0; it < kIter; ++it) {
+    for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
         const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
         int e;
         if (T::kStrideLog2 == 7) e = r & ((1 << S) - 1);                 // row = entry (sign variants share tlut[e])
         else e = 2 * r + ((lane >> 2) & 1);                              // 64-byte slots: two entries per row
-        v[it] = (r < kRows) ? __ldg(tlut + e) : 0u;
-        if (T::kFold && (r >> S)) v[it] ^= 0x8000u;                       // negate component 0 (low half)
+        t.v[it] = (r < TcqTableRegs<S>::kRows) ? __ldg(tlut + e) : 0u;
+        if (T::kFold && (r >> S)) t.v[it] ^= 0x8000u;                     // negate component 0 (low half)
     }
+}
+
+template <int S>
+__device__ __forceinline__ void tcq_table_store(uint32_t *tab, const TcqTableRegs<S> &t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll
-    for (int it = 0; it < kIter; ++it) {
+    for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
         const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
-        if (r < kRows) t4[r * 8 + (lane & 7)] = make_uint4(v[it], v[it], v[it], v[it]);
+        if (r < TcqTableRegs<S>::kRows) t4[r * 8 + (lane & 7)] = make_uint4(t.v[it], t.v[it], t.v[it], t.v[it]);
     }
+}
+
+template <int S>
+__device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *__restrict__ tlut) {
+    TcqTableRegs<S> t;
+    tcq_table_load<S>(t, tlut);
+    tcq_table_store<S>(tab, t);
 }
 
 template <int S>
@@ -142,6 +159,9 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     const int lane = threadIdx.x & 31;
     const int warp = warp_in_cta();
     QP_PHASE(0);
+    // codebook loads first: their L2 round trip runs under the range arithmetic and the weight-prefetch issue below
+    TcqTableRegs<S> tregs;
+    tcq_table_load<S>(tregs, tlut);
     // this CTA's contiguous range of each part; its warps interleave inside it
     unsigned loA, hiA;
     split_range(splitA, blockIdx.x, loA, hiA);
@@ -149,7 +169,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     uint32_t rawA[kGemvDepth][TcqGeom<KVA>::kRawWords];
     gemv_prefetch<KVA>(segA, runA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
     QP_PHASE(1);
-    tcq_build_table<S>(tab, tlut);
+    tcq_table_store<S>(tab, tregs);
     QP_PHASE(2);
     pdl_wait();  // x (and out) are produced by the preceding kernel
     QP_PHASE(3);
