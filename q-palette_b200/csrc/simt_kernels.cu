@@ -15,32 +15,40 @@ namespace qp {
 constexpr int kSimtThreads = 1024;
 constexpr int kSimtWarps = kSimtThreads / 32;
 
-template <int BITS>
+// Scalar codes of <= 5 bits are looked up two at a time (adjacent codes are one 2*BITS-bit field of the stream; the table
+// holds the fp16 pair), like the tensor-core layout's pair tables: half the lookups and no byte permutes.
+template <int BITS, int VEC>
 struct SimtTable {
-    static constexpr int kSL = (BITS <= 10) ? 7 : (17 - BITS);
-    static constexpr int kBytes = (1 << BITS) << kSL;
+    static constexpr bool kPair = (VEC == 1 && BITS <= 5);
+    static constexpr int kFieldBits = kPair ? 2 * BITS : BITS;
+    static constexpr int kSL = (kFieldBits <= 10) ? 7 : (17 - kFieldBits);
+    static constexpr int kBytes = (1 << kFieldBits) << kSL;
     static constexpr uint32_t kLaneMask = (1u << (kSL - 2)) - 1u;
 };
 
 template <int BITS, int VEC>
 __device__ __forceinline__ void simt_build_table(uint32_t *tab, const uint32_t *lc) {
-    using T = SimtTable<BITS>;
+    using T = SimtTable<BITS, VEC>;
     constexpr int copies = 1 << (T::kSL - 2);
-    for (int i = threadIdx.x; i < (1 << BITS) * copies; i += blockDim.x) {
+    const uint16_t *l16 = reinterpret_cast<const uint16_t *>(lc);
+    for (int i = threadIdx.x; i < (1 << T::kFieldBits) * copies; i += blockDim.x) {
         const int e = i / copies;
-        tab[i] = (VEC == 2) ? lc[e] : (uint32_t) reinterpret_cast<const uint16_t *>(lc)[e];
+        if (VEC == 2) tab[i] = lc[e];
+        else if (T::kPair) tab[i] = (uint32_t)l16[e & ((1 << BITS) - 1)] | ((uint32_t)l16[e >> BITS] << 16);
+        else tab[i] = (uint32_t)l16[e];
     }
 }
 
-// code I (0..31) of the thread's BITS-word little-endian stream, shifted left by SL and masked (table slot offset)
-template <int BITS, int I, int SL>
+// field I (FB bits wide, at bit I*FB) of the thread's BITS-word little-endian stream, shifted left by SL and masked
+// (table slot offset)
+template <int BITS, int FB, int I, int SL>
 __device__ __forceinline__ uint32_t simt_code_offset(const uint32_t (&w)[BITS]) {
-    constexpr int o = I * BITS;
+    constexpr int o = I * FB;
     constexpr int wi = o / 32, s = o % 32;
-    constexpr uint32_t mask = ((1u << BITS) - 1u) << SL;
+    constexpr uint32_t mask = ((1u << FB) - 1u) << SL;
     uint32_t v;
     if constexpr (s == 0) v = w[wi];
-    else if constexpr (s + BITS <= 32) v = w[wi] >> s;
+    else if constexpr (s + FB <= 32) v = w[wi] >> s;
     else v = __funnelshift_r(w[wi], w[wi + 1], s);
     return (v << SL) & mask;
 }
@@ -48,21 +56,22 @@ __device__ __forceinline__ uint32_t simt_code_offset(const uint32_t (&w)[BITS]) 
 // decode the 8 weights of group G (codes G*8/VEC ...) into 4 half2 registers
 template <int BITS, int VEC, int G>
 __device__ __forceinline__ void simt_group(const uint32_t (&w)[BITS], uint32_t tab, uint32_t (&h)[4]) {
-    constexpr int SL = SimtTable<BITS>::kSL;
-    if constexpr (VEC == 2) {
-        h[0] = lds_u32(tab + simt_code_offset<BITS, G * 4 + 0, SL>(w));
-        h[1] = lds_u32(tab + simt_code_offset<BITS, G * 4 + 1, SL>(w));
-        h[2] = lds_u32(tab + simt_code_offset<BITS, G * 4 + 2, SL>(w));
-        h[3] = lds_u32(tab + simt_code_offset<BITS, G * 4 + 3, SL>(w));
+    using T = SimtTable<BITS, VEC>;
+    constexpr int SL = T::kSL, FB = T::kFieldBits;
+    if constexpr (VEC == 2 || T::kPair) {  // one lookup per fp16 pair
+        h[0] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 0, SL>(w));
+        h[1] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 1, SL>(w));
+        h[2] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 2, SL>(w));
+        h[3] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 3, SL>(w));
     } else {
-        const uint32_t a0 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 0, SL>(w));
-        const uint32_t a1 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 1, SL>(w));
-        const uint32_t a2 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 2, SL>(w));
-        const uint32_t a3 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 3, SL>(w));
-        const uint32_t a4 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 4, SL>(w));
-        const uint32_t a5 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 5, SL>(w));
-        const uint32_t a6 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 6, SL>(w));
-        const uint32_t a7 = lds_u32(tab + simt_code_offset<BITS, G * 8 + 7, SL>(w));
+        const uint32_t a0 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 0, SL>(w));
+        const uint32_t a1 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 1, SL>(w));
+        const uint32_t a2 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 2, SL>(w));
+        const uint32_t a3 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 3, SL>(w));
+        const uint32_t a4 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 4, SL>(w));
+        const uint32_t a5 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 5, SL>(w));
+        const uint32_t a6 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 6, SL>(w));
+        const uint32_t a7 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 7, SL>(w));
         h[0] = __byte_perm(a0, a1, 0x5410);
         h[1] = __byte_perm(a2, a3, 0x5410);
         h[2] = __byte_perm(a4, a5, 0x5410);
@@ -112,7 +121,7 @@ template <int BITS, int VEC, bool GEMV>
 __global__ void __launch_bounds__(kSimtThreads, 1)
 simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const __half *__restrict__ x,
             const void *__restrict__ lut, int M, int K, int bs, int out_f32) {
-    using T = SimtTable<BITS>;
+    using T = SimtTable<BITS, VEC>;
     constexpr int NG = 4 * VEC;
     constexpr int kChunk = 32 * 32 * VEC;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -205,7 +214,7 @@ static int launch_simt(__half *out, const void *codes, const void *x, const void
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         configured = true;
     }
-    const size_t smem = (size_t)SimtTable<BITS>::kBytes + 4 * (size_t)(((1 << BITS) * VEC / 2) < 4 ? 4 : ((1 << BITS) * VEC / 2)) +
+    const size_t smem = (size_t)SimtTable<BITS, VEC>::kBytes + 4 * (size_t)(((1 << BITS) * VEC / 2) < 4 ? 4 : ((1 << BITS) * VEC / 2)) +
                         (GEMV ? (size_t)K * bs * 2 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem, "bs*K = %d*%d does not fit the shared-memory x stage", bs, K);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kSimtThreads), smem, st, out, (const uint32_t *)codes,
