@@ -59,19 +59,19 @@ __device__ __forceinline__ void simt_group(const uint32_t (&w)[BITS], uint32_t t
     using T = SimtTable<BITS, VEC>;
     constexpr int SL = T::kSL, FB = T::kFieldBits;
     if constexpr (VEC == 2 || T::kPair) {  // one lookup per fp16 pair
-        h[0] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 0, SL>(w));
-        h[1] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 1, SL>(w));
-        h[2] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 2, SL>(w));
-        h[3] = lds_u32(tab + simt_code_offset<BITS, FB, G * 4 + 3, SL>(w));
+        h[0] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 0, SL>(w) | tab));
+        h[1] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 1, SL>(w) | tab));
+        h[2] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 2, SL>(w) | tab));
+        h[3] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 3, SL>(w) | tab));
     } else {
-        const uint32_t a0 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 0, SL>(w));
-        const uint32_t a1 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 1, SL>(w));
-        const uint32_t a2 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 2, SL>(w));
-        const uint32_t a3 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 3, SL>(w));
-        const uint32_t a4 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 4, SL>(w));
-        const uint32_t a5 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 5, SL>(w));
-        const uint32_t a6 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 6, SL>(w));
-        const uint32_t a7 = lds_u32(tab + simt_code_offset<BITS, FB, G * 8 + 7, SL>(w));
+        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 0, SL>(w) | tab));
+        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 1, SL>(w) | tab));
+        const uint32_t a2 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 2, SL>(w) | tab));
+        const uint32_t a3 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 3, SL>(w) | tab));
+        const uint32_t a4 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 4, SL>(w) | tab));
+        const uint32_t a5 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 5, SL>(w) | tab));
+        const uint32_t a6 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 6, SL>(w) | tab));
+        const uint32_t a7 = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 8 + 7, SL>(w) | tab));
         h[0] = __byte_perm(a0, a1, 0x5410);
         h[1] = __byte_perm(a2, a3, 0x5410);
         h[2] = __byte_perm(a4, a5, 0x5410);
@@ -142,7 +142,7 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
     }
     __syncthreads();
     pdl_launch_dependents();
-    const uint32_t tab_lane = smem_u32(tab) + ((lane & T::kLaneMask) << 2);
+    const uint32_t tab_lane = (lane & T::kLaneMask) << 2;  // lane column; the table starts the dynamic shared memory (qp_dyn_smem)
     const uint32_t xs_addr = smem_u32(xs);
     const int row_words = BITS * K / 32 / VEC;
     const int nfull = K / kChunk, rem = K % kChunk;
