@@ -165,7 +165,7 @@ def run_reference(args):
     sample = f"per step: one 4096x4096 {QUANTIZER} dequantize+matvec (configs[0]) in C on {threads} threads; extrapolated to a token"
     print(json.dumps({
         "impl": "reference", "metric": "decode_tok_per_s", "value": v, "unit": "tok/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": avg * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": avg * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "quantizer": QUANTIZER},
         "cpu_baseline": {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
