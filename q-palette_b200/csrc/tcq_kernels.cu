@@ -48,7 +48,10 @@ struct TcqTable {
 #define QP_TCQ_FOLD 1
 #endif
     static constexpr bool kFold = (S == 9) && QP_TCQ_FOLD;
-    static constexpr int kStrideLog2 = (S == 11) ? 6 : 7;
+#ifndef QP_TCQ_STRIDE9
+#define QP_TCQ_STRIDE9 7  // experiments: 6 = 64-byte slots for S = 9 (16 copies, 2-way conflicts, no hash pre-shift, 64 KiB)
+#endif
+    static constexpr int kStrideLog2 = (S == 11) ? 6 : (S == 9 ? QP_TCQ_STRIDE9 : 7);
     static constexpr int kEntryBits = S + (kFold ? 1 : 0);
     static constexpr int kEntries = 1 << kEntryBits;
     static constexpr int kBytes = kEntries << kStrideLog2;            // 128 KiB for all three
@@ -74,11 +77,10 @@ __device__ __forceinline__ void tcq_table_load(TcqTableRegs<S> &t, const uint32_
 #pragma unroll
     for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
         const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
-        int e;
-        if (T::kStrideLog2 == 7) e = r & ((1 << S) - 1);                 // row = entry (sign variants share tlut[e])
-        else e = 2 * r + ((lane >> 2) & 1);                              // 64-byte slots: two entries per row
-        t.v[it] = (r < TcqTableRegs<S>::kRows) ? __ldg(tlut + e) : 0u;
-        if (T::kFold && (r >> S)) t.v[it] ^= 0x8000u;                     // negate component 0 (low half)
+        // 128-byte row r holds 128 >> kStrideLog2 entries; this lane's 16-byte chunk belongs to entry ef (incl. the fold bit)
+        const int ef = (r << (7 - T::kStrideLog2)) + ((lane & 7) >> (T::kStrideLog2 - 4));
+        t.v[it] = (r < TcqTableRegs<S>::kRows) ? __ldg(tlut + (ef & ((1 << S) - 1))) : 0u;
+        if (T::kFold && (ef >> S)) t.v[it] ^= 0x8000u;                    // negate component 0 (low half)
     }
 }
 
