@@ -171,7 +171,8 @@ int qp_step_advance(int *pos, int *history, const int *token, int max_hist, void
  *     x  = fp16(Hadamard(y * su) * had_scale)  (su optional)
  * itself while its first weight loads are in flight, then runs out += decode(W) x (out must be pre-zeroed / hold the
  * value to add to).  x_out_f16 (optional) receives x for sibling projections; zero1/zero2 name fp32 buffers to clear for
- * LATER launches (they must not be read or written by this one).  Replaces a qp_fused_norm_had launch + the x staging.
+ * LATER launches; they are cleared before the kernel waits for its predecessor, so neither this launch NOR the launch
+ * immediately before it on the stream may read or write them.  Replaces a qp_fused_norm_had launch + the x staging.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct qp_xprod {
     const void *src_f16;

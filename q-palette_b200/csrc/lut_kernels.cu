@@ -98,6 +98,7 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
     __syncthreads();
     lut_build_table<E, SPLIT>(tab, lc, r_single);
+    if (prod.mode != 0) xp_zero(prod);  // before the wait: see xprod.cuh
     pdl_wait();
     if (prod.mode == 0) stage_x(xs, x32, K, bs);
     else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);

@@ -12,6 +12,7 @@
 // 32-row strip are added to `out` with fp32 atomics when the run leaves the strip.
 // The decode is ALU/issue-bound on B200 (HBM bytes per SM-clock are 7x an RTX 4090's), so the inner loop is written
 // to minimise issued instructions per weight pair: see DESIGN.md "TCQ GEMV instruction budget".
+#include <type_traits>
 #include "qp_common.cuh"
 #include "tcq_bits.cuh"
 #include "gemv_common.cuh"
@@ -171,12 +172,24 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     uint32_t rawA[kGemvDepth][TcqGeom<KVA>::kRawWords];
     gemv_prefetch<KVA>(segA, runA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
     QP_PHASE(1);
-    tcq_table_store<S>(tab, tregs);
-    QP_PHASE(2);
-    pdl_wait();  // x (and out) are produced by the preceding kernel
-    QP_PHASE(3);
-    if (prod.mode == 0) stage_x(xs, x32, K, bs);
-    else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
+    float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
+    // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
+    auto finish_prologue = [&](auto ch_tag) {
+        constexpr int CH = decltype(ch_tag)::value;
+        XPre<CH> pre;
+        if (prod.mode != 0) {
+            xp_preload<CH>(pre, prod, K);
+            xp_zero(prod);
+        }
+        tcq_table_store<S>(tab, tregs);
+        QP_PHASE(2);
+        pdl_wait();  // x (and out) are produced by the preceding kernel
+        QP_PHASE(3);
+        if (prod.mode == 0) stage_x(xs, x32, K, bs);
+        else produce_x<CH>(xs, xscratch, red, prod, K, pre);
+    };
+    if (prod.mode == 0 || ((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
+    else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
     __syncthreads();
     QP_PHASE(4);
     pdl_launch_dependents();
@@ -431,6 +444,10 @@ extern "C" int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *cod
 }
 
 #ifdef QP_PROFILE_PHASES
+extern "C" int qp_debug_xphases(unsigned long long *host_out /* [256][8] */) {
+    QP_CUDA(cudaMemcpyFromSymbol(host_out, qp::g_xphase, sizeof(unsigned long long) * 256 * 8));
+    return QP_OK;
+}
 extern "C" int qp_debug_phases(unsigned long long *host_out /* [256][8] */) {
     QP_CUDA(cudaMemcpyFromSymbol(host_out, qp::g_phase, sizeof(unsigned long long) * 256 * 8));
     return QP_OK;

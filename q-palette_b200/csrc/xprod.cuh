@@ -11,6 +11,21 @@
 
 namespace qp {
 
+#ifdef QP_PROFILE_PHASES
+// debug build only: %globaltimer stamps inside produce_x (CTA-wide thread 0), read back with qp_debug_xphases
+__device__ unsigned long long g_xphase[256][8];
+__device__ __forceinline__ void xphase_stamp(int i) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_xphase[blockIdx.x][i] = t;
+    }
+}
+#define QP_XPHASE(i) xphase_stamp(i)
+#else
+#define QP_XPHASE(i)
+#endif
+
 struct XProd {
     int mode;                 // 0: x is given (plain staging); 1: produce x as described above
     const __half *src;        // h (n)
@@ -23,7 +38,7 @@ struct XProd {
     const __half *su;         // optional signs (n)
     float had_scale;
     __half *x_out;            // optional copy of x in natural order (for sibling projections sharing x)
-    float *zero1;             // accumulators to clear for later launches (must not be touched by this launch)
+    float *zero1;             // accumulators to clear for later launches (not touched by this launch or its predecessor)
     int zero1_count;
     float *zero2;
     int zero2_count;
@@ -73,25 +88,52 @@ __device__ __forceinline__ void xp_zero_slice(float *p, int count) {
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// accumulator-clearing duty of a fused launch, run BEFORE the programmatic-dependency wait (measured: ~0.4-0.7 us on the
+// critical path when done after it).  Safe for buffers that neither this launch nor the immediately preceding one touches:
+// a kernel's pre-wait code only starts once every CTA of its predecessor has passed its own wait, i.e. once the
+// predecessor's predecessor is complete.
+__device__ __forceinline__ void xp_zero(const XProd &p) {
+    xp_zero_slice(p.zero1, p.zero1_count);
+    xp_zero_slice(p.zero2, p.zero2_count);
+}
+
+// the inputs of produce_x that do NOT depend on the preceding kernel (per-row scales, norm weight, signs): a GEMV kernel
+// loads them before its programmatic-dependency wait, next to the weight prefetch, so that only h / acc are fetched in the
+// dependent part (every CTA reads the same few KB at the same time: the fewer of them after the wait, the better)
+template <int CH>
+struct XPre {
+    uint2 wv[CH], nv[CH], sv[CH];
+};
+template <int CH>
+__device__ __forceinline__ void xp_preload(XPre<CH> &r, const XProd &p, int n) {
+    const int nch = n >> 2, T = blockDim.x;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        const bool ok = c < nch;
+        r.wv[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const uint2 *>(p.wscale) + c) : make_uint2(0u, 0u);
+        r.nv[j] = (ok && p.norm_w) ? __ldg(reinterpret_cast<const uint2 *>(p.norm_w) + c) : make_uint2(0u, 0u);
+        r.sv[j] = (ok && p.su) ? __ldg(reinterpret_cast<const uint2 *>(p.su) + c) : make_uint2(0u, 0u);
+    }
+}
+
 // produce x (n = K values) into xs in the B-fragment order stage_x() uses (bs = 1).  v: n floats of shared scratch.
 // CH = ceil(n / 4 / blockDim.x) chunks of 4 consecutive elements per thread.
 template <int CH>
-__device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n) {
+__device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n, const XPre<CH> &pre) {
     const int nch = n >> 2, T = blockDim.x;
-    uint2 hv[CH], wv[CH], nv[CH], sv[CH];
+    QP_XPHASE(0);
+    uint2 hv[CH];
     float4 av[CH];
+    const uint2 (&wv)[CH] = pre.wv, (&nv)[CH] = pre.nv, (&sv)[CH] = pre.sv;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
         const bool ok = c < nch;
         hv[j] = ok ? __ldg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
         av[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const uint2 *>(p.wscale) + c) : make_uint2(0u, 0u);
-        nv[j] = (ok && p.norm_w) ? __ldg(reinterpret_cast<const uint2 *>(p.norm_w) + c) : make_uint2(0u, 0u);
-        sv[j] = (ok && p.su) ? __ldg(reinterpret_cast<const uint2 *>(p.su) + c) : make_uint2(0u, 0u);
     }
-    xp_zero_slice(p.zero1, p.zero1_count);
-    xp_zero_slice(p.zero2, p.zero2_count);
+    QP_XPHASE(1);  // loads issued, zero slices stored
     const __half hs = __float2half(p.acc_scale);
     float y[CH][4];
     float ss = 0.f;
@@ -118,6 +160,7 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
 #pragma unroll
         for (int e = 0; e < 4; ++e) ss += y[j][e] * y[j][e];
     }
+    QP_XPHASE(2);  // inputs arrived, residual added
     if (p.norm_w) {
         const float rstd = rsqrtf(xp_block_sum(ss, red) / (float)n + p.eps);
 #pragma unroll
@@ -129,6 +172,7 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
                 y[j][e] = __half2float(__hmul(__float2half(w4[e]), __float2half(y[j][e] * rstd)));
         }
     }
+    QP_XPHASE(3);  // normalised
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
@@ -142,7 +186,9 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
         if (c < nch) reinterpret_cast<float4 *>(v)[c] = make_float4(y[j][0], y[j][1], y[j][2], y[j][3]);
     }
     __syncthreads();
+    QP_XPHASE(4);  // strides < 128 done, in shared memory
     hadamard_smem(v, n, p.m, p.Kf, 7);
+    QP_XPHASE(5);  // Hadamard done
     // fp16 x in B-fragment order: element i = 32*kh + 16*kl + 8*b + 2*q + e  ->  word ((kh*4 + q)*4 + kl*2 + b), half e
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -166,11 +212,19 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
     }
 }
 
-// dispatch on the chunk count (n <= 15360 for 768 threads; larger n does not fit the shared-memory budget anyway)
+// dispatch on the chunk count (n <= 15360 for 768 threads; larger n does not fit the shared-memory budget anyway);
+// this form loads everything after the caller's dependency wait
 __device__ __forceinline__ void produce_x_dispatch(uint32_t *xs, float *v, float *red, const XProd &p, int n) {
     const int ch = ((n >> 2) + blockDim.x - 1) / blockDim.x;
-    if (ch <= 2) produce_x<2>(xs, v, red, p, n);
-    else produce_x<5>(xs, v, red, p, n);  // host guarantees n <= 5 * 4 * blockDim.x
+    if (ch <= 2) {
+        XPre<2> pre;
+        xp_preload<2>(pre, p, n);
+        produce_x<2>(xs, v, red, p, n, pre);
+    } else {  // host guarantees n <= 5 * 4 * blockDim.x
+        XPre<5> pre;
+        xp_preload<5>(pre, p, n);
+        produce_x<5>(xs, v, red, p, n, pre);
+    }
 }
 
 }  // namespace qp

@@ -313,9 +313,11 @@ class DecodeRunner:
             check(L.qp_rope_attention(p(self.attn), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads, sh.num_key_value_heads,
                                       sh.head_dim, self.max_seq, None, 0, st))
-            prod = xp(self.attn, su=ly["SU_o"], z1=self.acc_qkv, z2=self.acc_dn)
+            # fused launches clear accumulators BEFORE their dependency wait: only buffers the preceding launch does not
+            # touch (the attention kernel still reads acc_qkv while the o projection starts, so ug clears it instead)
+            prod = xp(self.attn, su=ly["SU_o"], z2=self.acc_dn)
             run_group([(ly["o"], 0)], self.acc_o, prod, self.x_h)
-            prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"])
+            prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"], z1=self.acc_qkv)
             run_group(ly["ug"], self.acc_ug, prod, self.x_h)
             hc, ho = ho, hc
             if self.silu_grid:
