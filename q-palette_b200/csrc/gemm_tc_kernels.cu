@@ -62,16 +62,18 @@ __device__ __forceinline__ void g_build_tcq_table(uint32_t *tab, const uint32_t 
 template <int KV, int S>
 struct GTcqDecoder {
     static constexpr int kE = KV;
-    __device__ static __forceinline__ uint32_t lookup(const uint8_t *tab_lane, uint32_t u) {
+    // address = (uniform table base) + ((slot offset) | (lane column)): one LOP3, no per-lookup pointer add
+    __device__ static __forceinline__ uint32_t lookup(const uint8_t *tab, uint32_t lane_col, uint32_t u) {
         using T = GTcqTable<S>;
         const uint32_t ts = u * (u * (1u << T::kShift) + (1u << T::kShift));
-        uint32_t w = *reinterpret_cast<const uint32_t *>(tab_lane + (ts & T::kMask));
+        uint32_t w = *reinterpret_cast<const uint32_t *>(tab + ((ts & T::kMask) | lane_col));
         if (!T::kFold) w ^= ((ts >> T::kShift) & 0x8000u);
         return w;
     }
     __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<KV>::kWords], int lane,
-                                                  const uint8_t *tab_lane, uint32_t (&frag)[4][4]) {
+                                                  const uint8_t *tab, uint32_t (&frag)[4][4]) {
         using G = TcqGeom<KV>;
+        const uint32_t lane_col = ((uint32_t)lane & GTcqTable<S>::kLaneMask) << 2;
         uint32_t send[4] = {tcq_send<KV, 0>(P), tcq_send<KV, 1>(P), tcq_send<KV, 2>(P), tcq_send<KV, 3>(P)};
         uint32_t n1[4], n2[4];
 #pragma unroll
@@ -87,7 +89,7 @@ struct GTcqDecoder {
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) frag[t][j] = lookup(tab_lane, u[t][j]);
+            for (int j = 0; j < 4; ++j) frag[t][j] = lookup(tab, lane_col, u[t][j]);
     }
 };
 
@@ -326,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
-    const uint8_t *tab_lane = tab + ((lane & Table::kLaneMask) << 2);
+    const uint8_t *tab_lane = tab;  // decoders add the lane column themselves (OR into the slot offset)
     pdl_wait();  // x / out come from the preceding kernel
     pdl_launch_dependents();
     QP_TC_T(t_loop);
@@ -535,19 +537,21 @@ template <int E>
 struct GLutDecoder {
     static constexpr int kE = E;
     template <int TI>
-    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab, uint32_t (&f)[4]) {
+    __device__ static __forceinline__ void tile(const uint32_t (&P)[TcqGeom<E>::kWords], const uint8_t *tab, uint32_t lc,
+                                                uint32_t (&f)[4]) {
         constexpr int SL = GLutTable<E>::kSL;
-        f[0] = *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, 0, SL>(P));
-        f[1] = *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, 1, SL>(P));
-        f[2] = *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, 2, SL>(P));
-        f[3] = *reinterpret_cast<const uint32_t *>(tab + lut_pair_offset<E, TI, 3, SL>(P));
+        f[0] = *reinterpret_cast<const uint32_t *>(tab + (lut_pair_offset<E, TI, 0, SL>(P) | lc));
+        f[1] = *reinterpret_cast<const uint32_t *>(tab + (lut_pair_offset<E, TI, 1, SL>(P) | lc));
+        f[2] = *reinterpret_cast<const uint32_t *>(tab + (lut_pair_offset<E, TI, 2, SL>(P) | lc));
+        f[3] = *reinterpret_cast<const uint32_t *>(tab + (lut_pair_offset<E, TI, 3, SL>(P) | lc));
     }
-    __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<E>::kWords], int, const uint8_t *tab_lane,
+    __device__ static __forceinline__ void decode(const uint32_t (&P)[TcqGeom<E>::kWords], int lane, const uint8_t *tab,
                                                   uint32_t (&frag)[4][4]) {
-        tile<0>(P, tab_lane, frag[0]);
-        tile<1>(P, tab_lane, frag[1]);
-        tile<2>(P, tab_lane, frag[2]);
-        tile<3>(P, tab_lane, frag[3]);
+        const uint32_t lc = ((uint32_t)lane & GLutTable<E>::kLaneMask) << 2;
+        tile<0>(P, tab, lc, frag[0]);
+        tile<1>(P, tab, lc, frag[1]);
+        tile<2>(P, tab, lc, frag[2]);
+        tile<3>(P, tab, lc, frag[3]);
     }
 };
 
