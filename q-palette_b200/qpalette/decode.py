@@ -235,8 +235,18 @@ class DecodeRunner:
         if self.p2p:
             # the four gathered buffers live in a region every peer maps; site = 4 * layer + {attn, o, act, down}
             from .peer import PeerRegion
-            self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4)], 4 * self.L + 4,
-                                     rank, world, process_group, self.dev)
+            try:
+                self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4)],
+                                         4 * self.L + 4, rank, world, process_group, self.dev)
+            except Exception as ex:  # e.g. CUDA IPC not permitted between these processes
+                self.region = None
+                print(f"[qpalette] rank {rank}: peer exchange unavailable ({ex}); using ncclAllGather", flush=True)
+            # every rank must take the same path
+            ok = torch.tensor([1 if self.region is not None else 0], device=self.dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
+                self.region, self.p2p = None, False
+        if self.p2p:
             self.attn = self.region.tensor("attn", torch.float16)
             self.acc_o = self.region.tensor("acc_o", torch.float32)
             self.act = self.region.tensor("act", torch.float16)

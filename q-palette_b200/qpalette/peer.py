@@ -28,27 +28,41 @@ class PeerRegion:
             off += (nbytes + 255) & ~255
         self.flags_offset = off
         self.nbytes = off + ((nsites * world * 4 + 255) & ~255)
-        base = ctypes.c_void_p()
-        check(lib().qp_peer_alloc(ctypes.byref(base), self.nbytes))
-        self.base = base.value
-        handle = ctypes.create_string_buffer(64)
-        check(lib().qp_peer_export(self.base, handle))
+        # every rank runs the same sequence of collectives whatever fails locally, and raises only at the end
+        err, raw = None, None
+        self.base, self.peer_bases = None, []
+        try:
+            base = ctypes.c_void_p()
+            check(lib().qp_peer_alloc(ctypes.byref(base), self.nbytes))
+            self.base = base.value
+            handle = ctypes.create_string_buffer(64)
+            check(lib().qp_peer_export(self.base, handle))
+            raw = handle.raw
+        except Exception as ex:
+            err = ex
         handles = [None] * world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self.peer_bases = []
-        for r, hb in enumerate(handles):
-            if r == rank:
-                self.peer_bases.append(self.base)
-            else:
-                ptr = ctypes.c_void_p()
-                check(lib().qp_peer_import(ctypes.create_string_buffer(hb, 64), ctypes.byref(ptr)))
-                self.peer_bases.append(ptr.value)
+        dist.all_gather_object(handles, raw, group=group)
+        if err is None and any(h is None for h in handles):
+            err = RuntimeError("a peer could not export its exchange region")
+        if err is None:
+            try:
+                for r, hb in enumerate(handles):
+                    if r == rank:
+                        self.peer_bases.append(self.base)
+                    else:
+                        ptr = ctypes.c_void_p()
+                        check(lib().qp_peer_import(ctypes.create_string_buffer(hb, 64), ctypes.byref(ptr)))
+                        self.peer_bases.append(ptr.value)
+            except Exception as ex:
+                err = ex
+        dist.barrier(group=group)  # every region is mapped everywhere before anyone pushes
+        if err is not None:
+            raise err
         i64 = dict(dtype=torch.int64, device=device)
         self.d_bases = torch.tensor(self.peer_bases, **i64)
         self.d_flags = torch.tensor([b + self.flags_offset for b in self.peer_bases], **i64)
         self.epoch = torch.zeros(nsites, dtype=torch.int32, device=device)
         self._keep = []
-        dist.barrier(group=group)  # every region is mapped everywhere before anyone pushes
 
     def tensor(self, name, dtype):
         """torch view of a buffer of the local region"""
