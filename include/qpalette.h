@@ -139,6 +139,13 @@ typedef struct qp_xchg {
 int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
                            float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
                            int do_had, float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
+/* Row-sharded SiLU*mul + Hadamard: acc_local / wscale_local = [up | gate] of this rank's I / nranks rows; one CTA per local
+ * 512-element block pushes its transformed block into the exchange buffer at xc->offset (I floats) of every rank, then every
+ * rank finishes the transform from its own copy: x_out = the complete fp16 vector on every rank.  *sync_counter: a local
+ * device word, 0 before the first call.  I / 512 must be a multiple of nranks (28*512: 2, 4; 28*1024: 2, 4, 8). */
+int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local, const void *wscale_local_f16, float acc_scale,
+                              const void *su_f16, int I, float had_scale, float *zero_ptr, int zero_count,
+                              unsigned *sync_counter, const qp_xchg *xc, void *stream);
 int qp_peer_alloc(void **ptr, size_t bytes);             /* cudaMalloc + clear */
 int qp_peer_free(void *ptr);
 int qp_peer_export(void *ptr, void *handle64);           /* 64-byte CUDA IPC handle of a qp_peer_alloc region */

@@ -115,7 +115,8 @@ __device__ __forceinline__ void peer_allgather(const XchgDev &xc) {
             reinterpret_cast<uint4 *>(xc.peer_base[peer] + off)[i] = val;
         }
     }
-    __threadfence_system();
+    // the CTA barrier orders every thread's stores before the flag writers; their release.sys store is cumulative over them
+    // (one system-scope release per peer instead of a system fence in each of the 1024 threads)
     __syncthreads();
     const int t = threadIdx.x;
     if (t < xc.nranks && t != xc.rank) {
@@ -387,6 +388,125 @@ silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *_
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) x_out[i * kSiluBlk + col] = __float2half(z[i] * had_scale);
+    }
+}
+
+// Row-sharded form of the kernel above: rank r holds the up / gate accumulators of rows [r, r+1) * I / nranks only.  It runs
+// one CTA per LOCAL 512-element block: SiLU*mul, sign, butterflies of stride < 512, then the block (fp32, 2 KB) is stored
+// into the exchange buffer `z` (I floats inside the peer-mapped region) of EVERY rank over NVLink and a per-(site, source)
+// counter on each peer is bumped (red.release.sys).  Once all I / 512 blocks have arrived (own blocks: local ticket; the
+// others: the peers' counters), every rank applies the cross-block factor to its share of the column positions and writes
+// the complete x.  Replaces SiLU*mul epilogue + all-gather + single-CTA Hadamard (3 launches, one NCCL call).
+// Counters only ever grow (launch k of a site waits for k * blocks-per-rank), so graph replays need no reset; the
+// accumulator-clearing duty is done by each CTA before it publishes (a peer that has seen all counters of this site knows
+// this rank's buffers are cleared).
+template <int KF, int R>
+__global__ void __launch_bounds__(kSiluThreads)
+silu_mul_had_grid_xchg_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, const __half *__restrict__ wscale,
+                              float acc_scale, const __half *__restrict__ su, int I, float had_scale,
+                              float *__restrict__ zero_ptr, int zero_count, unsigned *sync_counter, XchgDev xc) {
+    __shared__ __align__(16) float v[kSiluBlk];
+    pdl_wait();
+    pdl_launch_dependents();
+    constexpr int NB = KF * R;
+    const int nbl = gridDim.x;                 // local blocks = NB / nranks
+    const int Il = nbl * kSiluBlk;             // local rows
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int gb = xc.rank * nbl + b;          // global block
+    const int c = b * kSiluThreads + t;        // local chunk of 4 consecutive elements
+    const unsigned ep = *xc.epoch + 1u;        // every CTA reads it before any CTA can get past the barrier below
+    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
+    const float4 ag = reinterpret_cast<const float4 *>(acc + Il)[c];
+    const uint2 wu = reinterpret_cast<const uint2 *>(wscale)[c];
+    const uint2 wg = reinterpret_cast<const uint2 *>(wscale + Il)[c];
+    const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[gb * kSiluThreads + t] : make_uint2(0u, 0u);
+    if (zero_ptr) {
+        const int per = ((zero_count + nbl - 1) / nbl + 3) & ~3;
+        const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
+        zero_words4(zero_ptr + lo, hi - lo);
+    }
+    const __half hs = __float2half(acc_scale);
+    float w_u[4], w_g[4], s4[4], y[4];
+    unpack4(wu, w_u);
+    unpack4(wg, w_g);
+    unpack4(sv, s4);
+    const float u4[4] = {au.x, au.y, au.z, au.w}, g4[4] = {ag.x, ag.y, ag.z, ag.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float up = scaled_acc(u4[e], w_u[e], hs), g = scaled_acc(g4[e], w_g[e], hs);
+        const __half act = __float2half(g / (1.f + __expf(-g)));
+        y[e] = __half2float(__hmul(act, __float2half(up)));
+        if (su) y[e] *= s4[e];
+    }
+    had_warp128(y);
+    reinterpret_cast<float4 *>(v)[t] = make_float4(y[0], y[1], y[2], y[3]);
+    __syncthreads();
+    fwht_pass<2>(v, kSiluBlk, kHadLh0);
+    __syncthreads();
+    // publish block gb everywhere (own copy included)
+    const float4 zb = reinterpret_cast<const float4 *>(v)[t];
+    const size_t zoff = (size_t)xc.offset + ((size_t)gb * kSiluBlk + (size_t)t * 4) * sizeof(float);
+    for (int q = 0; q < xc.nranks; ++q) {
+        const int peer = (xc.rank + q) % xc.nranks;
+        *reinterpret_cast<float4 *>(xc.peer_base[peer] + zoff) = zb;
+    }
+    __syncthreads();  // orders the block's stores before the (cumulative) release.sys increments below
+    if (t < xc.nranks) {
+        // counter [site][source = this rank] on rank t (t == rank: the local count of this rank's own blocks)
+        unsigned *remote = xc.peer_flags[t] + xc.site * xc.nranks + xc.rank;
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(remote), "r"(1u) : "memory");
+        const unsigned target = ep * (unsigned)nbl;
+        const unsigned *mine = xc.peer_flags[xc.rank] + xc.site * xc.nranks + t;
+        unsigned cur;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(mine) : "memory");
+            if (clock64() - t0 > (1ll << 33)) __trap();  // a peer died: fail instead of hanging the GPU
+        } while ((int)(cur - target) < 0);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (b == 0 && t == 0) *xc.epoch = ep;
+    // cross-block factor on this CTA's share of the 512 column positions, all NB blocks from the local exchange buffer
+    const float *z = reinterpret_cast<const float *>(xc.peer_base[xc.rank] + xc.offset);
+    const int c_lo = b * kSiluBlk / nbl, c_hi = (b + 1) * kSiluBlk / nbl;
+    for (int col = c_lo + t; col < c_hi; col += kSiluThreads) {
+        float zz[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) zz[i] = __ldcg(z + i * kSiluBlk + col);
+        if (R > 1) {
+#pragma unroll
+            for (int k = 0; k < KF; ++k)
+#pragma unroll
+                for (int st = 1; st < R; st <<= 1)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if ((r & st) == 0) {
+                            const float a0 = zz[k * R + r], a1 = zz[k * R + (r | st)];
+                            zz[k * R + r] = a0 + a1;
+                            zz[k * R + (r | st)] = a0 - a1;
+                        }
+        }
+        if (KF == 28) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float u[14], w[14], sju[14], sjw[14];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    u[j] = zz[j * R + r];
+                    w[j] = zz[(14 + j) * R + r];
+                }
+                jacobsthal14(u, sju);
+                jacobsthal14(w, sjw);
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    zz[j * R + r] = (sju[j] + u[j]) + (sjw[j] - w[j]);
+                    zz[(14 + j) * R + r] = (sju[j] - u[j]) - (sjw[j] + w[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) x_out[i * kSiluBlk + col] = __float2half(zz[i] * had_scale);
     }
 }
 
@@ -781,6 +901,41 @@ extern "C" int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wsc
                        (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, had_scale, zero_ptr, zero_count,
                        sync_counter));
     return check_launch("silu_mul_had_grid");
+}
+
+extern "C" int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local, const void *wscale_local_f16, float acc_scale,
+                                         const void *su_f16, int I, float had_scale, float *zero_ptr, int zero_count,
+                                         unsigned *sync_counter, const qp_xchg *xc, void *stream) {
+    QP_CHECK_ARG(x_out_f16 && acc_local && wscale_local_f16 && sync_counter, "NULL pointer argument");
+    QP_CHECK_ARG(xc && xc->peer_base && xc->peer_flags && xc->epoch, "NULL exchange descriptor");
+    QP_CHECK_ARG(xc->nranks >= 2 && xc->nranks <= 32 && xc->rank >= 0 && xc->rank < xc->nranks, "bad rank %d of %d", xc->rank, xc->nranks);
+    int m, Kf;
+    int rc = had_dims(I, m, Kf);
+    if (rc != QP_OK) return rc;
+    QP_CHECK_ARG(m % kSiluBlk == 0, "I = %d: needs a power-of-two factor >= 512", I);
+    const int R = m / kSiluBlk, NB = Kf * R;
+    QP_CHECK_ARG(NB % xc->nranks == 0, "I / 512 = %d blocks do not split over %d ranks", NB, xc->nranks);
+    QP_CHECK_ARG(xc->offset % 16 == 0, "exchange buffer must be 16-byte aligned");
+    void (*kern)(__half *, const float *, const __half *, float, const __half *, int, float, float *, int, unsigned *, XchgDev) =
+        nullptr;
+    if (Kf == 28 && R == 1) kern = silu_mul_had_grid_xchg_kernel<28, 1>;
+    else if (Kf == 28 && R == 2) kern = silu_mul_had_grid_xchg_kernel<28, 2>;
+    else if (Kf == 1 && R == 8) kern = silu_mul_had_grid_xchg_kernel<1, 8>;
+    else if (Kf == 1 && R == 16) kern = silu_mul_had_grid_xchg_kernel<1, 16>;
+    QP_CHECK_ARG(kern != nullptr, "I = %d = %d * %d * 512 is not instantiated for the multi-CTA kernel", I, Kf, R);
+    XchgDev d;
+    d.peer_base = (unsigned char *const *)xc->peer_base;
+    d.peer_flags = (unsigned *const *)xc->peer_flags;
+    d.epoch = xc->epoch + xc->site;
+    d.offset = xc->offset;
+    d.slice_bytes = xc->slice_bytes;
+    d.rank = xc->rank;
+    d.nranks = xc->nranks;
+    d.site = xc->site;
+    QP_CUDA(launch_pdl(kern, dim3(NB / xc->nranks), dim3(kSiluThreads), 0, (cudaStream_t)stream, (__half *)x_out_f16, acc_local,
+                       (const __half *)wscale_local_f16, acc_scale, (const __half *)su_f16, I, had_scale, zero_ptr, zero_count,
+                       sync_counter, d));
+    return check_launch("silu_mul_had_grid_xchg");
 }
 
 extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,

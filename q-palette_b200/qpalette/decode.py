@@ -236,7 +236,7 @@ class DecodeRunner:
             # the four gathered buffers live in a region every peer maps; site = 4 * layer + {attn, o, act, down}
             from .peer import PeerRegion
             try:
-                self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4)],
+                self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4), ("z", I * 4)],
                                          4 * self.L + 4, rank, world, process_group, self.dev)
             except Exception as ex:  # e.g. CUDA IPC not permitted between these processes
                 self.region = None
@@ -268,6 +268,9 @@ class DecodeRunner:
         self.scratch = torch.zeros(4096, dtype=torch.uint8, device=self.dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=self.dev)  # ticket of the multi-CTA SiLU*mul/Hadamard kernel
         self.silu_grid = silu_grid_supported(self.I)
+        # row-sharded form: the I / 512 blocks must split evenly over the ranks (and the shape be instantiated)
+        self.silu_grid_tp = (self.p2p and self.I % (512 * world) == 0 and
+                             any(self.I == kf * r * 512 for kf, r in ((28, 1), (28, 2), (1, 8), (1, 16))))
         self.graph = None
         self.lm_head_bytes = self.lm_head.numel() * 2
         self.launches_per_step = 0
@@ -399,12 +402,19 @@ class DecodeRunner:
                 check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i,
                                         p(self.acc_dn), self.acc_dn.numel(), st))
             else:
-                act_dst = p(self.act) + 2 * rank * Il if p2p else p(self.act_loc)
-                check(L.qp_scale_epilogue(act_dst, p(self.acc_ug), p(ly["W_ug"]), 1, 2 * Il, S, _cabi.EPI_SILU_MUL, st))
-                if gather:
-                    torch.distributed.all_gather_into_tensor(self.act, self.act_loc, group=self.pg)
-                norm_had(4 * li + 2, "act", p(self.x_i), p(self.act), 0, None, None, 0.0, None, 0.0, p(ly["SU_dp"]), I, s_i, 1,
-                         p(self.acc_dn), self.acc_dn.numel())
+                if p2p and self.silu_grid_tp:
+                    # SiLU*mul + NVLink exchange of the transformed 512-blocks + cross-block Hadamard factor in one launch
+                    xc = self.region.xchg("z", 4 * li + 2)
+                    keep.append(xc)
+                    check(L.qp_silu_mul_had_grid_xchg(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i,
+                                                      p(self.acc_dn), self.acc_dn.numel(), p(self.sync), ctypes.byref(xc), st))
+                else:
+                    act_dst = p(self.act) + 2 * rank * Il if p2p else p(self.act_loc)
+                    check(L.qp_scale_epilogue(act_dst, p(self.acc_ug), p(ly["W_ug"]), 1, 2 * Il, S, _cabi.EPI_SILU_MUL, st))
+                    if gather:
+                        torch.distributed.all_gather_into_tensor(self.act, self.act_loc, group=self.pg)
+                    norm_had(4 * li + 2, "act", p(self.x_i), p(self.act), 0, None, None, 0.0, None, 0.0, p(ly["SU_dp"]), I,
+                             s_i, 1, p(self.acc_dn), self.acc_dn.numel())
             ly["down"].launch(p(self.acc_dn) + 4 * rank * Ho, p(self.x_i), st)
             if gather:
                 torch.distributed.all_gather_into_tensor(self.acc_dn, self.acc_dn[rank * Ho:(rank + 1) * Ho], group=self.pg)
