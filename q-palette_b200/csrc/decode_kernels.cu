@@ -336,9 +336,9 @@ silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *_
     fwht_pass<2>(v, kSiluBlk, kHadLh0);  // strides 128, 256 across the 4 warps
     __syncthreads();
     reinterpret_cast<float4 *>(acc)[c] = reinterpret_cast<const float4 *>(v)[t];  // publish block b
-    __threadfence();
     __syncthreads();
     if (t == 0) {
+        __threadfence();  // cumulative over the CTA's stores (ordered before it by the barrier): one fence, not 128
         const unsigned old = atomicAdd(sync_counter, 1u);
         const unsigned target = old - old % NB + NB;
         unsigned cur;
