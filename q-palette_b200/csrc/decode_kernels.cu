@@ -520,13 +520,27 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
                       float acc_scale, const float *__restrict__ inv_freq, __half *__restrict__ kcache,
                       __half *__restrict__ vcache, const int *__restrict__ pos_ptr, int H, int Hkv, int D, int max_seq,
                       float *__restrict__ zero_ptr, int zero_count) {
-    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[2][D] | scores[max_seq]
+    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[8][D] | scores[max_seq]
     __shared__ float red[32];
-    float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *part = sm + 3 * D, *sc = sm + 5 * D;
+    float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *part = sm + 3 * D, *sc = sm + 11 * D;
+    const int head = blockIdx.x, kvh = head / (H / Hkv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kAttnThreads / 32;
+    // Cached rows [0, pos) and pos itself were written by earlier decode steps, not by the preceding kernel: the first 64
+    // positions' K and V rows (8 per warp, 8 bytes per lane) are fetched before the dependency wait, so that a short context
+    // costs one memory round trip that overlaps the q/k/v epilogue + RoPE below.
+    const int pos = *pos_ptr;
+    uint2 kpre[8], vpre[8];
+    if (D == 128) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = warp + u * nw;
+            const size_t row = ((size_t)t * Hkv + kvh) * D;
+            kpre[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + row)[lane] : make_uint2(0u, 0u);
+            vpre[u] = (t < pos) ? reinterpret_cast<const uint2 *>(vcache + row)[lane] : make_uint2(0u, 0u);
+        }
+    }
     pdl_wait();
     pdl_launch_dependents();
-    const int head = blockIdx.x, kvh = head / (H / Hkv);
-    const int pos = *pos_ptr;
     if (zero_ptr && blockIdx.x == 0) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
     const int d = threadIdx.x;
@@ -558,7 +572,6 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     __syncthreads();
     const float scale = rsqrtf((float)D);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kAttnThreads / 32;
     // scores over cached positions [0, pos): lane owns dims 4*lane..+3 (D = 128) -- generic D handled by the strided loop
     if (D == 128) {
         const float4 q4 = reinterpret_cast<const float4 *>(q)[lane];
@@ -567,7 +580,8 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int t = t0 + u * nw;
-                kv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
+                if (t0 == warp) kv[u] = kpre[u];  // first batch: prefetched
+                else kv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -609,7 +623,41 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     sum = block_sum(sum, red);
     __syncthreads();
-    // output: two halves of the positions per dim, 8 loads in flight
+    if (D == 128) {
+        // output: warp w takes positions w, w + 8, ... (one 256-byte V row per load, 8 in flight), lane owns dims 4*lane..+3;
+        // the 8 partial rows are summed through shared memory
+        float o4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t0 = warp; t0 < pos; t0 += nw * 8) {
+            uint2 vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nw;
+                if (t0 == warp) vv[u] = vpre[u];
+                else vv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(vcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * nw;
+                if (t < pos) {
+                    float v4[4];
+                    unpack4(vv[u], v4);
+                    const float w = sc[t];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o4[e] += w * v4[e];
+                }
+            }
+        }
+        reinterpret_cast<float4 *>(part + warp * D)[lane] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        __syncthreads();
+        if (threadIdx.x < D) {
+            float o = sc[pos] * vn[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < kAttnThreads / 32; ++w) o += part[w * D + threadIdx.x];
+            attn_out[head * D + threadIdx.x] = __float2half(o / sum);
+        }
+        return;
+    }
+    // generic head size: two halves of the positions per dim, 8 loads in flight
     const int dd = threadIdx.x % D, part_id = threadIdx.x / D, nparts = (kAttnThreads / D) >= 2 ? 2 : 1;
     if (part_id < nparts) {
         float o = 0.f;
@@ -943,7 +991,7 @@ extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const
                                  int Hkv, int D, int max_seq, float *zero_ptr, int zero_count, void *stream) {
     QP_CHECK_ARG(attn_out_f16 && acc_qkv && wscale_f16 && inv_freq && kcache_f16 && vcache_f16 && pos_ptr, "NULL pointer");
     QP_CHECK_ARG(D <= 128 && D % 2 == 0 && H % Hkv == 0 && kAttnThreads % D == 0, "unsupported head geometry H=%d Hkv=%d D=%d", H, Hkv, D);
-    const size_t smem = (size_t)(5 * D + max_seq) * 4;
+    const size_t smem = (size_t)(11 * D + max_seq) * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "max_seq = %d too large for the single-pass attention kernel", max_seq);
     static bool configured = false;
     if (!configured) {

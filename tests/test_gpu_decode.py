@@ -144,6 +144,11 @@ def _ref_layer_step(r, x_in_h, pos, caches):
     f = lambda a: a.float().cpu().numpy().astype(np.float64)
 
     def proj_W(p):
+        if getattr(p, "_Wref", None) is None:
+            p._Wref = proj_W_decode(p)
+        return p._Wref
+
+    def proj_W_decode(p):
         if p.kind == "tcq_ldlq":
             return O.tcq_decode(t(p.codes1), t(p.lut), p.M, p.K, p.KV1, p.S)
         if p.kind == "combt_ldlq":
@@ -191,12 +196,14 @@ def _ref_layer_step(r, x_in_h, pos, caches):
 
 
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged", "uniform_merged_grid_silu"])
+@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged", "uniform_merged_grid_silu", "uniform_merged_d128"])
 def test_decode_step_matches_restatement(variant, fused):
     from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
-    # intermediate 4096 = 8 * 512 takes the multi-CTA SiLU*mul/Hadamard kernel in the fused list, 28 * 128 the single-CTA one
+    # intermediate 4096 = 8 * 512 takes the multi-CTA SiLU*mul/Hadamard kernel in the fused list, 28 * 128 the single-CTA one;
+    # 4 heads of 128 take the attention kernel's head_dim-128 path (prefetched K/V rows), 8 heads of 64 the generic one
     inter = 4096 if variant == "uniform_merged_grid_silu" else 28 * 128
-    shape = LlamaShape(hidden_size=512, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=8,
+    heads = 4 if variant == "uniform_merged_d128" else 8
+    shape = LlamaShape(hidden_size=512, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=heads,
                        num_key_value_heads=2, vocab_size=1024)
     if variant.startswith("uniform_merged"):
         qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 2
@@ -207,12 +214,13 @@ def test_decode_step_matches_restatement(variant, fused):
         qd["1_self_attn.q_proj"] = ("ldlq_2_6_none_1.0", "1")
         qd["1_mlp.down_proj"] = ("tcomb_7_8_0.5_none_0.9", "0")
         mi = [["merge_kv"], []]
-    r = DecodeRunner(shape, qd, mi, max_seq=16, seed=3, fused=fused)
+    long_ctx = variant == "uniform_merged_d128"  # > 64 positions: the attention loops go past their prefetched batch
+    r = DecodeRunner(shape, qd, mi, max_seq=80 if long_ctx else 16, seed=3, fused=fused)
     assert r.fused == fused
     caches = [([], []) for _ in r.layers]
     tok = 5
     r.reset(tok)
-    for step in range(3):
+    for step in range(70 if long_ctx else 3):
         x0 = r.embed[tok].float().cpu().numpy()
         _, logits_ref = _ref_layer_step(r, x0, step, caches)
         r.step()
