@@ -302,16 +302,17 @@ silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *_
                          const __half *__restrict__ su, int I, float had_scale, float *__restrict__ zero_ptr, int zero_count,
                          unsigned *sync_counter) {
     __shared__ __align__(16) float v[kSiluBlk];
-    pdl_wait();
-    pdl_launch_dependents();
     constexpr int NB = KF * R;
     const int b = blockIdx.x, t = threadIdx.x;
     const int c = b * kSiluThreads + t;  // this thread's chunk of 4 consecutive elements
-    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
-    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
+    // scales and signs do not depend on the preceding kernel: fetched before the dependency wait
     const uint2 wu = reinterpret_cast<const uint2 *>(wscale)[c];
     const uint2 wg = reinterpret_cast<const uint2 *>(wscale + I)[c];
     const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    pdl_wait();
+    pdl_launch_dependents();
+    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
+    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
     if (zero_ptr) {  // this CTA's slice of the accumulators to clear for later launches
         const int per = ((zero_count + NB - 1) / NB + 3) & ~3;
         const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
@@ -539,25 +540,29 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
             vpre[u] = (t < pos) ? reinterpret_cast<const uint2 *>(vcache + row)[lane] : make_uint2(0u, 0u);
         }
     }
+    // likewise independent of the preceding kernel: the per-row scales and the rotary angle of this position
+    const int d = threadIdx.x;
+    const int half = D / 2;
+    const int pd = d < half ? d + half : d - half;
+    const int iq = head * D, ik = H * D + kvh * D, iv = (H + Hkv) * D + kvh * D;
+    float wq = 0.f, wqp = 0.f, wk = 0.f, wkp = 0.f, wv = 0.f, c16 = 0.f, s16 = 0.f;
+    if (d < D) {
+        wq = __half2float(wscale[iq + d]), wqp = __half2float(wscale[iq + pd]), wk = __half2float(wscale[ik + d]);
+        wkp = __half2float(wscale[ik + pd]), wv = __half2float(wscale[iv + d]);
+        const float fr = inv_freq[d % half];
+        double snd, csd;  // precise range reduction (the build uses --use_fast_math)
+        sincos((double)pos * (double)fr, &snd, &csd);
+        // fp16 rounding of cos/sin as the fp16 reference graph does
+        c16 = __half2float(__float2half((float)csd)), s16 = __half2float(__float2half((float)snd));
+    }
     pdl_wait();
     pdl_launch_dependents();
     if (zero_ptr && blockIdx.x == 0) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
-    const int d = threadIdx.x;
     if (d < D) {
-        const int half = D / 2;
-        const int pd = d < half ? d + half : d - half;
-        const int iq = head * D, ik = H * D + kvh * D, iv = (H + Hkv) * D + kvh * D;
         // all loads first
         const float aq = acc_qkv[iq + d], aqp = acc_qkv[iq + pd], ak = acc_qkv[ik + d], akp = acc_qkv[ik + pd], av = acc_qkv[iv + d];
-        const float wq = __half2float(wscale[iq + d]), wqp = __half2float(wscale[iq + pd]), wk = __half2float(wscale[ik + d]),
-                    wkp = __half2float(wscale[ik + pd]), wv = __half2float(wscale[iv + d]);
-        const float fr = inv_freq[d % half];
         const float sgn = d < half ? -1.f : 1.f;
-        double snd, csd;  // precise range reduction (the build uses --use_fast_math)
-        sincos((double)pos * (double)fr, &snd, &csd);
-        // fp16 rounding of cos/sin and of the products as the fp16 reference graph does
-        const float c16 = __half2float(__float2half((float)csd)), s16 = __half2float(__float2half((float)snd));
         const float qa = scaled_acc(aq, wq, hs), qb = scaled_acc(aqp, wqp, hs);
         const float ka = scaled_acc(ak, wk, hs), kb = scaled_acc(akp, wkp, hs);
         q[d] = __half2float(__float2half(qa * c16 + sgn * qb * s16));
