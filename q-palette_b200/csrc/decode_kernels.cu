@@ -146,6 +146,18 @@ fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, co
                       float *__restrict__ zero_ptr, int zero_count, XchgDev xc) {
     extern __shared__ __align__(16) float v[];
     __shared__ float red[32];
+    const int nch = n >> 2;
+    uint2 hv[CH], wv[CH], nv[CH], sv[CH];
+    float4 av[CH];
+    // scales, norm weight and signs do not depend on the preceding kernel: fetched before the dependency wait
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * kDecThreads;
+        const bool ok = c < nch;
+        wv[j] = (ok && acc) ? reinterpret_cast<const uint2 *>(wscale)[c] : make_uint2(0u, 0u);
+        nv[j] = (ok && norm_w) ? reinterpret_cast<const uint2 *>(norm_w)[c] : make_uint2(0u, 0u);
+        sv[j] = (ok && su) ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    }
     pdl_wait();
     pdl_launch_dependents();
     if (xc.nranks > 1) {
@@ -154,18 +166,12 @@ fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, co
         zero_ptr = nullptr;
         peer_allgather(xc);  // completes `h` / `acc` (whichever is the row-sharded one) in place
     }
-    const int nch = n >> 2;
-    uint2 hv[CH], wv[CH], nv[CH], sv[CH];
-    float4 av[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * kDecThreads;
         const bool ok = c < nch;
         hv[j] = ok ? reinterpret_cast<const uint2 *>(h)[c] : make_uint2(0u, 0u);
         av[j] = (ok && acc) ? reinterpret_cast<const float4 *>(acc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[j] = (ok && acc) ? reinterpret_cast<const uint2 *>(wscale)[c] : make_uint2(0u, 0u);
-        nv[j] = (ok && norm_w) ? reinterpret_cast<const uint2 *>(norm_w)[c] : make_uint2(0u, 0u);
-        sv[j] = (ok && su) ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
     }
     if (zero_ptr) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
