@@ -187,6 +187,8 @@ def main():
                          "MSQ qdict + merge_info for Llama-3.1-8B (configs/*.json, BASELINE.json configs[2])")
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (invalid as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true",
+                    help="debug: separate RMSNorm/Hadamard launches instead of the fused GEMV prologues (9 launches per layer)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -223,7 +225,7 @@ def main():
         q_name = QUANTIZER
     runner = DecodeRunner(shape, qdict, merge_info,
                           max_seq=max_seq, seed=0, rank=rank if tp > 1 else 0, world=tp, process_group=pg if tp > 1 else None,
-                          num_layers=args.layers)
+                          num_layers=args.layers, fused=not args.unfused)
     runner.capture()
     stream = torch.cuda.current_stream()
 
