@@ -248,3 +248,36 @@ def test_scale_epilogue(ops):
     up, gate = ref[:, :128], ref[:, 128:]
     ref2 = torch.nn.functional.silu(gate.float()).half() * up
     assert torch.allclose(out2.float(), ref2.float(), rtol=2e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ reference operator names
+def test_reference_operator_names(ops):
+    """the reference's shape-templated `torch.ops.ours_lib.*` names (lib/linear/__init__.py:43-420) resolve onto the C ABI:
+    same schemas, same results as the direct wrappers, fake (meta) implementations for tracing, AttributeError for garbage"""
+    rng = np.random.default_rng(5)
+    M, K, KV, S = 256, 512, 6, 9
+    buf = cuda(rng.integers(0, 256, size=M * K * KV // 16, dtype=np.uint8))
+    tl = cuda(rand_tlut(rng, S))
+    x = cuda(rng.standard_normal((1, K)).astype(np.float16))
+    op = ops.resolve(f"decompress_gemm_tcq_{M}_1_{K}_{S}_{KV}")
+    assert op is getattr(torch.ops.ours_lib, f"decompress_gemm_tcq_{M}_1_{K}_{S}_{KV}")
+    y = op(buf.view(torch.int16), x, tl)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (1, M)
+    assert torch.allclose(y, ops.tcq_gemv(buf, x, tl, M, K, S, KV), rtol=1e-4, atol=1e-4)  # fp32 atomics: order varies
+    W = ops.resolve(f"decompress_tcq_{S}_{KV}")(buf.view(torch.int16), tl, M, K)
+    assert W.dtype == torch.float16 and tuple(W.shape) == (M, K)
+    assert bits_equal(W, O.tcq_decode(buf.cpu().numpy(), tl.cpu().numpy(), M, K, KV, S))
+    # vector quantizer, tensor-core layout
+    R = 6
+    lut = cuda(rng.standard_normal((1 << R, 2)).astype(np.float16))
+    q = cuda(rng.integers(0, 256, size=M * K * R // 16, dtype=np.uint8))
+    y2 = ops.resolve(f"decompress_gemm_{M}_1_{K}_{R}_vq2")(q.view(torch.int32).view(M, -1), x, lut)
+    assert torch.allclose(y2, ops.lut_gemv(q, x, lut, M, K, R, 2), rtol=1e-4, atol=1e-4)
+    # meta / fake implementation (what torch.compile traces)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    b16 = buf.view(torch.int16)
+    with FakeTensorMode() as mode:
+        fy = op(mode.from_tensor(b16), mode.from_tensor(x), mode.from_tensor(tl))
+        assert tuple(fy.shape) == (1, M) and fy.dtype == torch.float32
+    with pytest.raises(AttributeError):
+        ops.resolve("decompress_gemm_tcq_not_an_op")
