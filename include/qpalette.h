@@ -158,6 +158,10 @@ int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *wscale_f16, f
                     int I, float had_scale, float *zero_ptr, int zero_count, void *stream);
 /* same result on I / 512 cooperating CTAs (I = 28*512, 28*1024 or 2^k >= 4096): `acc` is consumed (its first I words are
  * used as exchange space), *sync_counter is a device word that is 0 before the first call and reserved to one stream. */
+/* same result on ONE thread-block cluster of <= 8 CTAs exchanging their blocks through distributed shared memory (no scratch,
+ * `acc` untouched); same shapes as qp_silu_mul_had_grid */
+int qp_silu_mul_had_cluster(void *x_out_f16, const float *acc, const void *wscale_f16, float acc_scale, const void *su_f16,
+                            int I, float had_scale, float *zero_ptr, int zero_count, void *stream);
 int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wscale_f16, float acc_scale, const void *su_f16, int I,
                          float had_scale, float *zero_ptr, int zero_count, unsigned *sync_counter, void *stream);
 /* acc_qkv = [q | k | v] fp32 GEMV sums: Wscale epilogue, RoPE, KV-cache append at *pos_ptr, causal attention of the new

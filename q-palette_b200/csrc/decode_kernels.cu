@@ -398,6 +398,93 @@ silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *_
     }
 }
 
+// Thread-block-cluster form of the kernel above: ONE cluster of CL <= 8 CTAs, each owning NB / CL of the 512-element blocks.
+// The transformed blocks stay in the owning CTA's shared memory; after a hardware cluster barrier every CTA reads the NB
+// values of its column positions straight out of its peers' shared memory (DSMEM) -- no global exchange buffer, no atomic
+// ticket, no L2 round trip between the two phases.  `acc` is not modified.
+template <int KF, int R, int CL>
+__global__ void __launch_bounds__((KF * R / CL) * kSiluThreads)
+silu_mul_had_cluster_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, const __half *__restrict__ wscale,
+                            float acc_scale, const __half *__restrict__ su, int I, float had_scale,
+                            float *__restrict__ zero_ptr, int zero_count) {
+    constexpr int NB = KF * R, BPC = NB / CL, T = BPC * kSiluThreads, NE = BPC * kSiluBlk;
+    static_assert(NB % CL == 0 && CL <= 8, "blocks must split evenly over a portable cluster");
+    __shared__ __align__(16) float v[NE];
+    const int b = blockIdx.x, t = threadIdx.x;  // the grid is one cluster: blockIdx.x = rank in the cluster
+    const int c = b * T + t;                    // this thread's chunk of 4 consecutive elements
+    const uint2 wu = reinterpret_cast<const uint2 *>(wscale)[c];
+    const uint2 wg = reinterpret_cast<const uint2 *>(wscale + I)[c];
+    const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
+    pdl_wait();
+    pdl_launch_dependents();
+    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
+    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
+    if (zero_ptr) {
+        const int per = ((zero_count + CL - 1) / CL + 3) & ~3;
+        const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
+        zero_words4(zero_ptr + lo, hi - lo);
+    }
+    const __half hs = __float2half(acc_scale);
+    float w_u[4], w_g[4], s4[4], y[4];
+    unpack4(wu, w_u);
+    unpack4(wg, w_g);
+    unpack4(sv, s4);
+    const float u4[4] = {au.x, au.y, au.z, au.w}, g4[4] = {ag.x, ag.y, ag.z, ag.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float up = scaled_acc(u4[e], w_u[e], hs), g = scaled_acc(g4[e], w_g[e], hs);
+        const __half act = __float2half(g / (1.f + __expf(-g)));
+        y[e] = __half2float(__hmul(act, __float2half(up)));
+        if (su) y[e] *= s4[e];
+    }
+    had_warp128(y);  // strides 1..64
+    reinterpret_cast<float4 *>(v)[t] = make_float4(y[0], y[1], y[2], y[3]);
+    __syncthreads();
+    fwht_pass<2>(v, NE, kHadLh0);  // strides 128, 256 inside every 512-block of this CTA
+    cluster_sync_all();            // all blocks of all CTAs are final (also orders this CTA's own shared-memory writes)
+    // cross-block factor on this CTA's share of the 512 column positions; block i lives in CTA i / BPC
+    const int c_lo = b * kSiluBlk / CL, c_hi = (b + 1) * kSiluBlk / CL;
+    for (int col = c_lo + t; col < c_hi; col += T) {
+        float z[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) z[i] = ld_dsmem_f32(v + (i % BPC) * kSiluBlk + col, (unsigned)(i / BPC));
+        if (R > 1) {
+#pragma unroll
+            for (int k = 0; k < KF; ++k)
+#pragma unroll
+                for (int st = 1; st < R; st <<= 1)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if ((r & st) == 0) {
+                            const float a0 = z[k * R + r], a1 = z[k * R + (r | st)];
+                            z[k * R + r] = a0 + a1;
+                            z[k * R + (r | st)] = a0 - a1;
+                        }
+        }
+        if (KF == 28) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float u[14], w[14], sju[14], sjw[14];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    u[j] = z[j * R + r];
+                    w[j] = z[(14 + j) * R + r];
+                }
+                jacobsthal14(u, sju);
+                jacobsthal14(w, sjw);
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    z[j * R + r] = (sju[j] + u[j]) + (sjw[j] - w[j]);
+                    z[(14 + j) * R + r] = (sju[j] - u[j]) - (sjw[j] + w[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) x_out[i * kSiluBlk + col] = __float2half(z[i] * had_scale);
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its blocks
+}
+
 // Row-sharded form of the kernel above: rank r holds the up / gate accumulators of rows [r, r+1) * I / nranks only.  It runs
 // one CTA per LOCAL 512-element block: SiLU*mul, sign, butterflies of stride < 512, then the block (fp32, 2 KB) is stored
 // into the exchange buffer `z` (I floats inside the peer-mapped region) of EVERY rank over NVLink and a per-(site, source)
@@ -960,6 +1047,37 @@ extern "C" int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wsc
                        (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, had_scale, zero_ptr, zero_count,
                        sync_counter));
     return check_launch("silu_mul_had_grid");
+}
+
+extern "C" int qp_silu_mul_had_cluster(void *x_out_f16, const float *acc, const void *wscale_f16, float acc_scale,
+                                       const void *su_f16, int I, float had_scale, float *zero_ptr, int zero_count,
+                                       void *stream) {
+    QP_CHECK_ARG(x_out_f16 && acc && wscale_f16, "NULL pointer argument");
+    int m, Kf;
+    int rc = had_dims(I, m, Kf);
+    if (rc != QP_OK) return rc;
+    QP_CHECK_ARG(m % kSiluBlk == 0, "I = %d: the cluster kernel needs a power-of-two factor >= 512 (use qp_silu_mul_had)", I);
+    const int R = m / kSiluBlk;
+#define QP_LAUNCH_CLUSTER(KF_, R_, CL_)                                                                                   \
+    do {                                                                                                                  \
+        auto kern = silu_mul_had_cluster_kernel<KF_, R_, CL_>;                                                            \
+        static bool configured = false;                                                                                   \
+        if (!configured) {                                                                                                \
+            QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));                       \
+            configured = true;                                                                                            \
+        }                                                                                                                 \
+        QP_CUDA(launch_pdl_cluster(kern, dim3(CL_), dim3((KF_ * R_ / CL_) * kSiluThreads), CL_, 0, (cudaStream_t)stream,  \
+                                   (__half *)x_out_f16, acc, (const __half *)wscale_f16, acc_scale,                       \
+                                   (const __half *)su_f16, I, had_scale, zero_ptr, zero_count));                          \
+        return check_launch("silu_mul_had_cluster");                                                                      \
+    } while (0)
+    if (Kf == 28 && R == 1) QP_LAUNCH_CLUSTER(28, 1, 7);
+    if (Kf == 28 && R == 2) QP_LAUNCH_CLUSTER(28, 2, 8);
+    if (Kf == 1 && R == 8) QP_LAUNCH_CLUSTER(1, 8, 8);
+    if (Kf == 1 && R == 16) QP_LAUNCH_CLUSTER(1, 16, 8);
+    if (Kf == 1 && R == 32) QP_LAUNCH_CLUSTER(1, 32, 8);
+#undef QP_LAUNCH_CLUSTER
+    return fail(QP_ERR_ARG, "I = %d = %d * %d * 512 is not instantiated for the cluster kernel (use qp_silu_mul_had)", I, Kf, R);
 }
 
 extern "C" int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local, const void *wscale_local_f16, float acc_scale,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "qp_peer_import": [_vp, _vp],
     "qp_peer_close": [_vp],
     "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
+    "qp_silu_mul_had_cluster": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_grid": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp],
     "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "qp_gemv_f16": [_vp, _vp, _vp, _i, _i, _vp],

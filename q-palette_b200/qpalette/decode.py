@@ -333,9 +333,9 @@ class DecodeRunner:
             prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"], z1=self.acc_qkv)
             run_group(ly["ug"], self.acc_ug, prod, self.x_h)
             hc, ho = ho, hc
-            if self.silu_grid:
-                check(L.qp_silu_mul_had_grid(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0,
-                                             p(self.sync), st))
+            if self.silu_grid:  # one thread-block cluster, blocks exchanged through distributed shared memory
+                check(L.qp_silu_mul_had_cluster(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0,
+                                                st))
             else:
                 check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
             ly["down"].launch(p(self.acc_dn), p(self.x_i), st)

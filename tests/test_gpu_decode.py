@@ -273,6 +273,15 @@ def test_silu_mul_had_grid(I):
     x1 = torch.empty(I, dtype=torch.float16, device=dev)
     check(lib().qp_silu_mul_had(x1.data_ptr(), t(acc).data_ptr(), ws_d.data_ptr(), S, su_d.data_ptr(), I, had_scale, None, 0, st))
     single = x1.float().cpu().numpy()
+    # thread-block-cluster form (DSMEM exchange): same result, `acc` untouched
+    acc_d, x_c = t(acc.copy()), torch.empty(I, dtype=torch.float16, device=dev)
+    zero.fill_(1.0)
+    check(lib().qp_silu_mul_had_cluster(x_c.data_ptr(), acc_d.data_ptr(), ws_d.data_ptr(), S, su_d.data_ptr(), I, had_scale,
+                                        zero.data_ptr(), zero.numel(), st))
+    torch.cuda.synchronize()
+    assert float(zero.abs().sum().item()) == 0.0
+    assert np.array_equal(acc_d.cpu().numpy(), acc)
+    outs.append(x_c.float().cpu().numpy())
     for o in outs:
         assert np.linalg.norm(o - ref) / np.linalg.norm(ref) <= 1e-3
         assert np.linalg.norm(o - single) / np.linalg.norm(single) <= 1e-3
