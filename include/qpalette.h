@@ -10,6 +10,7 @@
 #ifndef QPALETTE_H
 #define QPALETTE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -146,6 +147,9 @@ int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeback, const 
 int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local, const void *wscale_local_f16, float acc_scale,
                               const void *su_f16, int I, float had_scale, float *zero_ptr, int zero_count,
                               unsigned *sync_counter, const qp_xchg *xc, void *stream);
+/* how long the in-kernel flag waits of the exchange kernels spin before the kernel traps (so that a dead peer fails the
+ * CUDA context instead of hanging the GPU); per device, default ~60 s, ms <= 0 = wait forever */
+int qp_set_spin_timeout_ms(long long ms);
 int qp_peer_alloc(void **ptr, size_t bytes);             /* cudaMalloc + clear */
 int qp_peer_free(void *ptr);
 int qp_peer_export(void *ptr, void *handle64);           /* 64-byte CUDA IPC handle of a qp_peer_alloc region */
@@ -164,11 +168,13 @@ int qp_silu_mul_had_cluster(void *x_out_f16, const float *acc, const void *wscal
                             int I, float had_scale, float *zero_ptr, int zero_count, void *stream);
 int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wscale_f16, float acc_scale, const void *su_f16, int I,
                          float had_scale, float *zero_ptr, int zero_count, unsigned *sync_counter, void *stream);
-/* acc_qkv = [q | k | v] fp32 GEMV sums: Wscale epilogue, RoPE, KV-cache append at *pos_ptr, causal attention of the new
- * token over the cache; one CTA per query head (IncoherentSdpaAttention.forward, lib/linear/incoherent_linear.py:110-203) */
+/* acc_qkv = [q | k | v] fp32 GEMV sums ([q | v | k] when qvk_order != 0: a merge_qv layer, whose Wscale_qkv the reference
+ * stores in that order, lib/linear/incoherent_linear.py:211-213): Wscale epilogue, RoPE, KV-cache append at *pos_ptr, causal
+ * attention of the new token over the cache; one CTA per query head (IncoherentSdpaAttention.forward, :110-203).
+ * *pos_ptr >= max_seq is clamped to the last cache row (memory safety only; the host API refuses to step that far). */
 int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,
                       const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H, int Hkv,
-                      int D, int max_seq, float *zero_ptr, int zero_count, void *stream);
+                      int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *stream);
 /* fp16 GEMV for the unquantized lm_head: out (rows) fp32 = W (rows, K) @ x (K) */
 int qp_gemv_f16(float *out, const void *W_f16, const void *x_f16, int rows, int K, void *stream);
 int qp_argmax(int *token_out, const float *logits, int n, void *scratch, void *stream);

@@ -17,6 +17,15 @@ namespace qp {
 
 constexpr int kDecThreads = 1024;
 
+// spin limit (SM clock cycles) of the cross-GPU / cross-CTA flag waits before the kernel traps instead of hanging the GPU;
+// 0 = wait forever.  Host-settable (qp_set_spin_timeout_ms): a rank under a profiler, a first-touch page fault or an
+// 80-layer graph instantiation can legitimately lag its peers by seconds.
+__device__ unsigned long long g_spin_limit_cycles = 120000000000ull;  // ~60 s at 2 GHz
+__device__ __forceinline__ bool spin_expired(long long t0) {
+    const unsigned long long lim = g_spin_limit_cycles;
+    return lim != 0ull && (unsigned long long)(clock64() - t0) > lim;
+}
+
 __device__ __forceinline__ float block_sum(float v, float *red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -127,7 +136,7 @@ __device__ __forceinline__ void peer_allgather(const XchgDev &xc) {
         const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(mine) : "memory");
-            if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a peer died; fail instead of hanging the GPU
+            if (spin_expired(t0)) __trap();  // a peer died: fail instead of hanging the GPU (limit: qp_set_spin_timeout_ms)
         } while ((int)(cur - ep) < 0);
     }
     __syncthreads();
@@ -555,7 +564,7 @@ silu_mul_had_grid_xchg_kernel(__half *__restrict__ x_out, const float *__restric
         const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(mine) : "memory");
-            if (clock64() - t0 > (1ll << 33)) __trap();  // a peer died: fail instead of hanging the GPU
+            if (spin_expired(t0)) __trap();  // a peer died: fail instead of hanging the GPU
         } while ((int)(cur - target) < 0);
         __threadfence_system();
     }
@@ -613,7 +622,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ acc_qkv, const __half *__restrict__ wscale,
                       float acc_scale, const float *__restrict__ inv_freq, __half *__restrict__ kcache,
                       __half *__restrict__ vcache, const int *__restrict__ pos_ptr, int H, int Hkv, int D, int max_seq,
-                      float *__restrict__ zero_ptr, int zero_count) {
+                      int qvk_order, float *__restrict__ zero_ptr, int zero_count) {
     extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[8][D] | scores[max_seq]
     __shared__ float red[32];
     float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *part = sm + 3 * D, *sc = sm + 11 * D;
@@ -622,7 +631,9 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     // Cached rows [0, pos) and pos itself were written by earlier decode steps, not by the preceding kernel: the first 64
     // positions' K and V rows (8 per warp, 8 bytes per lane) are fetched before the dependency wait, so that a short context
     // costs one memory round trip that overlaps the q/k/v epilogue + RoPE below.
-    const int pos = *pos_ptr;
+    // a position past the cache capacity would write out of bounds (cache rows and the score array hold max_seq entries):
+    // clamp to the last row -- the host API refuses to step that far (DecodeRunner.step), this only keeps memory safe
+    const int pos = min(*pos_ptr, max_seq - 1);
     uint2 kpre[8], vpre[8];
     if (D == 128) {
 #pragma unroll
@@ -637,7 +648,8 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     const int d = threadIdx.x;
     const int half = D / 2;
     const int pd = d < half ? d + half : d - half;
-    const int iq = head * D, ik = H * D + kvh * D, iv = (H + Hkv) * D + kvh * D;
+    // accumulator / Wscale order: q | k | v, or q | v | k for a merge_qv layer (lib/linear/incoherent_linear.py:211-213)
+    const int iq = head * D, ik = (qvk_order ? H + Hkv : H) * D + kvh * D, iv = (qvk_order ? H : H + Hkv) * D + kvh * D;
     float wq = 0.f, wqp = 0.f, wk = 0.f, wkp = 0.f, wv = 0.f, c16 = 0.f, s16 = 0.f;
     if (d < D) {
         wq = __half2float(wscale[iq + d]), wqp = __half2float(wscale[iq + pd]), wk = __half2float(wscale[ik + d]);
@@ -932,11 +944,10 @@ static int fused_norm_had_impl(void *x_out_f16, void *h_f16, int h_writeback, co
                  int, int, float, int, float *, int, XchgDev) =
         ch <= 1 ? fused_norm_had_kernel<1> : ch <= 2 ? fused_norm_had_kernel<2> : ch <= 4 ? fused_norm_had_kernel<4>
                                                                                        : fused_norm_had_kernel<8>;
-    static bool configured[4] = {false, false, false, false};
+    static DeviceOnce configured[4];
     const int ki = ch <= 1 ? 0 : ch <= 2 ? 1 : ch <= 4 ? 2 : 3;
-    if (!configured[ki]) {
+    if (configured[ki].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-        configured[ki] = true;
     }
     QP_CUDA(launch_pdl(kern, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16, (__half *)h_f16,
                        h_writeback, acc, (const __half *)wscale_f16, acc_scale, (const __half *)norm_w_f16, eps,
@@ -1015,11 +1026,10 @@ extern "C" int qp_silu_mul_had(void *x_out_f16, const float *acc, const void *ws
     void (*kern)(__half *, const float *, const __half *, float, const __half *, int, int, int, float, float *, int) =
         ch <= 1 ? silu_mul_had_kernel<1> : ch <= 2 ? silu_mul_had_kernel<2> : ch <= 4 ? silu_mul_had_kernel<4>
                                                                                      : silu_mul_had_kernel<8>;
-    static bool configured[4] = {false, false, false, false};
+    static DeviceOnce configured[4];
     const int ki = ch <= 1 ? 0 : ch <= 2 ? 1 : ch <= 4 ? 2 : 3;
-    if (!configured[ki]) {
+    if (configured[ki].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-        configured[ki] = true;
     }
     QP_CUDA(launch_pdl(kern, dim3(1), dim3(kDecThreads), smem, (cudaStream_t)stream, (__half *)x_out_f16, acc,
                        (const __half *)wscale_f16, acc_scale, (const __half *)su_f16, I, m, Kf, had_scale, zero_ptr,
@@ -1061,10 +1071,9 @@ extern "C" int qp_silu_mul_had_cluster(void *x_out_f16, const float *acc, const 
 #define QP_LAUNCH_CLUSTER(KF_, R_, CL_)                                                                                   \
     do {                                                                                                                  \
         auto kern = silu_mul_had_cluster_kernel<KF_, R_, CL_>;                                                            \
-        static bool configured = false;                                                                                   \
-        if (!configured) {                                                                                                \
+        static DeviceOnce configured;                                                                                   \
+        if (configured.first()) {                                                                                                \
             QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));                       \
-            configured = true;                                                                                            \
         }                                                                                                                 \
         QP_CUDA(launch_pdl_cluster(kern, dim3(CL_), dim3((KF_ * R_ / CL_) * kSiluThreads), CL_, 0, (cudaStream_t)stream,  \
                                    (__half *)x_out_f16, acc, (const __half *)wscale_f16, acc_scale,                       \
@@ -1117,29 +1126,27 @@ extern "C" int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local
 
 extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,
                                  const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H,
-                                 int Hkv, int D, int max_seq, float *zero_ptr, int zero_count, void *stream) {
+                                 int Hkv, int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *stream) {
     QP_CHECK_ARG(attn_out_f16 && acc_qkv && wscale_f16 && inv_freq && kcache_f16 && vcache_f16 && pos_ptr, "NULL pointer");
     QP_CHECK_ARG(D <= 128 && D % 2 == 0 && H % Hkv == 0 && kAttnThreads % D == 0, "unsupported head geometry H=%d Hkv=%d D=%d", H, Hkv, D);
     const size_t smem = (size_t)(11 * D + max_seq) * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "max_seq = %d too large for the single-pass attention kernel", max_seq);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(rope_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-        configured = true;
     }
     QP_CUDA(launch_pdl(rope_attention_kernel, dim3(H), dim3(kAttnThreads), smem, (cudaStream_t)stream, (__half *)attn_out_f16,
                        acc_qkv, (const __half *)wscale_f16, acc_scale, inv_freq, (__half *)kcache_f16,
-                       (__half *)vcache_f16, pos_ptr, H, Hkv, D, max_seq, zero_ptr, zero_count));
+                       (__half *)vcache_f16, pos_ptr, H, Hkv, D, max_seq, qvk_order, zero_ptr, zero_count));
     return check_launch("rope_attention");
 }
 
 extern "C" int qp_gemv_f16(float *out, const void *W_f16, const void *x_f16, int rows, int K, void *stream) {
     QP_CHECK_ARG(out && W_f16 && x_f16, "NULL pointer argument");
     QP_CHECK_ARG(K % 8 == 0 && (size_t)K * 2 <= 96 * 1024, "K = %d unsupported", K);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(gemv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
     }
     QP_CUDA(launch_pdl(gemv_f16_kernel, dim3(sm_count() * 2), dim3(512), (size_t)K * 2, (cudaStream_t)stream, out,
                        (const __half *)W_f16, (const __half *)x_f16, rows, K));
@@ -1167,4 +1174,14 @@ extern "C" int qp_step_advance(int *pos, int *history, const int *token, int max
     QP_CHECK_ARG(pos && token, "NULL pointer argument");
     QP_CUDA(launch_pdl(step_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, pos, history, token, max_hist));
     return check_launch("step_advance");
+}
+
+/* limit of the in-kernel flag waits of the peer-exchange kernels on the CURRENT device; ms <= 0 disables the trap */
+extern "C" int qp_set_spin_timeout_ms(long long ms) {
+    int dev = 0, khz = 0;
+    QP_CUDA(cudaGetDevice(&dev));
+    QP_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    const unsigned long long cyc = ms <= 0 ? 0ull : (unsigned long long)ms * (unsigned long long)(khz > 0 ? khz : 2000000);
+    QP_CUDA(cudaMemcpyToSymbol(qp::g_spin_limit_cycles, &cyc, sizeof(cyc)));
+    return QP_OK;
 }

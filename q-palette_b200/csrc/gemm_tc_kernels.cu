@@ -641,10 +641,9 @@ static int launch_tc(TcPart a, TcPart b, float *out, const void *x, const void *
     }
     size_t smem = fixed + (size_t)nstages * stage_bytes + ((size_t)slot_bytes << np_log2);
     if (((size_t)slot_bytes << np_log2) < (size_t)(128 - npad) * 128) smem += (size_t)(128 - npad) * 128;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048));
-        configured = true;
     }
     CUtensorMap xmap, pmapA, pmapB;
     int rc = make_x_map(&xmap, x, bs, K, npad);

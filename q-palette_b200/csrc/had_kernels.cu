@@ -83,11 +83,10 @@ extern "C" int qp_hadamard(void *y, const void *x, const void *su_f16, int rows,
     void (*kern)(void *, const void *, const __half *, int, int, int, float);
     if (x_is_f32) kern = y_is_f32 ? hadamard_kernel<true, true> : hadamard_kernel<true, false>;
     else kern = y_is_f32 ? hadamard_kernel<false, true> : hadamard_kernel<false, false>;
-    static bool configured[4] = {false, false, false, false};
+    static DeviceOnce configured[4];
     const int ki = (x_is_f32 ? 2 : 0) + (y_is_f32 ? 1 : 0);
-    if (!configured[ki]) {
+    if (configured[ki].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        configured[ki] = true;
     }
     QP_CUDA(launch_pdl(kern, dim3(rows), dim3(kHadThreads), smem, st, y, x, (const __half *)su_f16, n, m, Kf, scale));
     return check_launch("hadamard");

@@ -131,10 +131,9 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
                            int bs, const XProd &prod, cudaStream_t st) {
     using T = LutTable<E, SPLIT>;
     auto kern = lut_gemv_kernel<E, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
-        configured = true;
     }
     const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2 +
                         (prod.mode ? (size_t)K * 4 : 0);
@@ -149,10 +148,9 @@ template <int E, bool SPLIT>
 static int launch_lut_dequant(PackSegment seg, __half *W, const void *lut, int r_single, int K, cudaStream_t st) {
     using T = LutTable<E, SPLIT>;
     auto kern = lut_dequant_kernel<E, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        configured = true;
     }
     kern<<<sm_count(), kGemvThreads, T::kBytes + 4 * lut_compact_words(E, r_single), st>>>(
         seg, make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), W, lut, r_single, K);

@@ -5,6 +5,7 @@ namespace qp {
 
 std::atomic<uint64_t> g_launches{0};
 
+
 char *last_error_buf() {
     static thread_local char buf[512] = {0};
     return buf;

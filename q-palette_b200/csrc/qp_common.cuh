@@ -20,6 +20,18 @@ int fail(int code, const char *fmt, ...);     // formats into last_error_buf and
 extern std::atomic<uint64_t> g_launches;      // kernels launched by this library
 int sm_count();                               // cached cudaDevAttrMultiProcessorCount of the current device
 
+// one-time, PER-DEVICE setup guard of a kernel instantiation: cudaFuncSetAttribute (the opt-in to > 48 KB of dynamic
+// shared memory) is a per-device property, and one process may drive several GPUs (`with torch.cuda.device(...)`).
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown: just set it again
+        const unsigned long long bit = 1ull << dev;
+        return (done.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+    }
+};
+
 #define QP_CHECK_ARG(cond, ...)                                  \
     do {                                                         \
         if (!(cond)) return ::qp::fail(QP_ERR_ARG, __VA_ARGS__); \

@@ -136,10 +136,9 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
     coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), kCompactWords);
     __syncthreads();
     simt_build_table<BITS, VEC>(tab, lc);
-    if (GEMV) {
-        pdl_wait();
-        coop_copy_words(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
-    }
+    // the dequantise form waits too: its output may alias a stream-ordered temporary the preceding kernel still reads
+    pdl_wait();
+    if (GEMV) coop_copy_words(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
     __syncthreads();
     pdl_launch_dependents();
     const uint32_t tab_lane = (lane & T::kLaneMask) << 2;  // lane column; the table starts the dynamic shared memory (qp_dyn_smem)
@@ -209,10 +208,9 @@ template <int BITS, int VEC, bool GEMV>
 static int launch_simt(__half *out, const void *codes, const void *x, const void *lut, int M, int K, int bs,
                        int out_f32, cudaStream_t st) {
     auto kern = simt_kernel<BITS, VEC, GEMV>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        configured = true;
     }
     const size_t smem = (size_t)SimtTable<BITS, VEC>::kBytes + 4 * (size_t)(((1 << BITS) * VEC / 2) < 4 ? 4 : ((1 << BITS) * VEC / 2)) +
                         (GEMV ? (size_t)K * bs * 2 : 0);

@@ -273,10 +273,9 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     auto kern = tcq_gemv_kernel<KVA, KVB, S>;
     const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (prod.mode ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
-        configured = true;
     }
     const int nctas = sm_count() * kGemvCtasPerSM;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
@@ -288,10 +287,9 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
 template <int KVA, int KVB, int S>
 static int launch_dequant(const TcqLaunch &L, __half *W, const void *tlut, int K, cudaStream_t st) {
     auto kern = tcq_dequant_kernel<KVA, KVB, S>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        configured = true;
     }
     const int nwarps = sm_count() * kTcqWarps;
     kern<<<sm_count(), kTcqThreads, TcqTable<S>::kBytes, st>>>(

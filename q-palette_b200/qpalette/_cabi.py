@@ -35,6 +35,7 @@ SIGNATURES = {
     "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
     "qp_fused_norm_had_xchg": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp, _vp],
     "qp_silu_mul_had_grid_xchg": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp, _vp],
+    "qp_set_spin_timeout_ms": [ctypes.c_longlong],
     "qp_peer_alloc": [_vp, ctypes.c_size_t],
     "qp_peer_free": [_vp],
     "qp_peer_export": [_vp, _vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
     "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_cluster": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_grid": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp],
-    "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "qp_gemv_f16": [_vp, _vp, _vp, _i, _i, _vp],
     "qp_argmax": [_vp, _vp, _i, _vp, _vp],
     "qp_embed": [_vp, _vp, _vp, _i, _vp],

@@ -200,7 +200,10 @@ class DecodeRunner:
             elif "merge_kv" in merges:
                 ly["qkv"] = [(mk(q, H, H), 0), (mk(k, H, 2 * kvd, [kvd, kvd]), Hq)]
             elif "merge_qv" in merges:
-                raise NotImplementedError("merge_qv is not used by the shipped MSQ solutions")
+                # accumulator (and Wscale) order q | v | k for this layer, as the reference stores Wscale_qkv for merge_qv
+                # (lib/linear/incoherent_linear.py:211-213); the attention kernel is told through `qvk_order`
+                ly["qkv"] = [(mk(q, H, H + kvd, [H, kvd]), 0), (mk(k, H, kvd), Hq + Hk)]
+                ly["qvk"] = 1
             else:
                 ly["qkv"] = [(mk(q, H, H), 0), (mk(k, H, kvd), Hq), (mk(v, H, kvd), Hq + Hk)]
             ly["o"] = mk(o, H, H)
@@ -212,13 +215,16 @@ class DecodeRunner:
             ly["down"] = mk(down, I, H)
             ly["norm1"], ly["norm2"] = torch.ones(H, **f16), torch.ones(H, **f16)
             ly["SU_qkv"], ly["SU_o"], ly["SU_ug"], ly["SU_dp"] = signs(H), signs(H), signs(H), signs(I)
-            # Wscale ~ 1/sqrt(K)/s keeps activations O(1) through random-init layers (Wscale is per output row)
-            ly["W_qkv"] = wscale(Hq + 2 * Hk) * (H ** -0.5)
-            ly["W_o"] = wscale(H // world) * (H ** -0.5)
-            ly["W_ug"] = wscale(2 * Il) * (H ** -0.5)
-            ly["W_dp"] = wscale(H // world) * (I ** -0.5)
-            for name in ("W_qkv", "W_o", "W_ug", "W_dp"):
-                ly[name] = ly[name].to(torch.float16)
+            # Wscale ~ 1/sqrt(K)/s keeps activations O(1) through random-init layers (Wscale is per output row).
+            # Drawn at FULL width on every rank (same generator state everywhere) and sliced like the weight rows, so a
+            # row-sharded run reproduces the world = 1 model exactly.
+            def rows_of(full, sizes):
+                return torch.cat([full[r0:r0 + n] for r0, n in shard_plan(sizes, rank, world)]).contiguous()
+
+            ly["W_qkv"] = rows_of((wscale(H + 2 * kvd) * (H ** -0.5)).to(torch.float16), [H, kvd, kvd])
+            ly["W_o"] = rows_of((wscale(H) * (H ** -0.5)).to(torch.float16), [H])
+            ly["W_ug"] = rows_of((wscale(2 * I) * (H ** -0.5)).to(torch.float16), [I, I])
+            ly["W_dp"] = rows_of((wscale(H) * (I ** -0.5)).to(torch.float16), [H])
             ly["kc"] = torch.zeros((max_seq, shape.num_key_value_heads // world, shape.head_dim), **f16)
             ly["vc"] = torch.zeros_like(ly["kc"])
             for p in [pp for pp, _ in ly["qkv"]] + [ly["o"]] + [pp for pp, _ in ly["ug"]] + [ly["down"]]:
@@ -272,6 +278,7 @@ class DecodeRunner:
         self.silu_grid_tp = (self.p2p and self.I % (512 * world) == 0 and
                              any(self.I == kf * r * 512 for kf, r in ((28, 1), (28, 2), (1, 8), (1, 16))))
         self.graph = None
+        self.steps_done = 0          # host-side count of positions written since reset(): the KV cache holds max_seq rows
         self.lm_head_bytes = self.lm_head.numel() * 2
         self.launches_per_step = 0
         self._prepare_full_scales()
@@ -325,7 +332,7 @@ class DecodeRunner:
                 hc, ho = ho, hc
             check(L.qp_rope_attention(p(self.attn), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads, sh.num_key_value_heads,
-                                      sh.head_dim, self.max_seq, None, 0, st))
+                                      sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
             # fused launches clear accumulators BEFORE their dependency wait: only buffers the preceding launch does not
             # touch (the attention kernel still reads acc_qkv while the o projection starts, so ug clears it instead)
             prod = xp(self.attn, su=ly["SU_o"], z2=self.acc_dn)
@@ -386,7 +393,7 @@ class DecodeRunner:
             attn_dst = p(self.attn) + 2 * rank * Hq if p2p else (p(self.attn) if world == 1 else p(self.attn_loc))
             check(L.qp_rope_attention(attn_dst, p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
-                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, None, 0, st))
+                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
             if gather:
                 torch.distributed.all_gather_into_tensor(self.attn, self.attn_loc, group=self.pg)
             norm_had(4 * li + 0, "attn", p(self.x_h), p(self.attn), 0, None, None, 0.0, None, 0.0, p(ly["SU_o"]), H, s_h, 1,
@@ -440,6 +447,7 @@ class DecodeRunner:
     def reset(self, token=1):
         self.token.fill_(token)
         self.pos.zero_()
+        self.steps_done = 0
 
     def capture(self):
         self.reset()
@@ -457,6 +465,12 @@ class DecodeRunner:
         return self
 
     def step(self):
+        """one decode token.  Raises once the KV cache is full: position max_seq would be written past the cache rows and
+        the attention kernel's score array (the kernel itself only clamps, to stay memory-safe)."""
+        if self.steps_done >= self.max_seq:
+            raise RuntimeError(f"decode position {self.steps_done} exceeds max_seq={self.max_seq}: build the DecodeRunner "
+                               "with a larger max_seq or call reset()")
+        self.steps_done += 1
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -464,6 +478,8 @@ class DecodeRunner:
 
     def generate(self, n_tokens, token=1):
         """greedy decode n_tokens from `token`; returns the generated ids (host list)."""
+        if n_tokens > self.max_seq:
+            raise RuntimeError(f"generate({n_tokens}) exceeds max_seq={self.max_seq}")
         self.reset(token)
         for _ in range(n_tokens):
             self.step()

@@ -8,7 +8,11 @@ import torch
 
 from oracle import qp_oracle as O
 
+import _restate as R
+
 pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north_star: layer outputs within fp16 tolerance, rel-L2 <= 1e-3 on the same packed inputs
 
 
 def rel_l2(a, b):
@@ -44,9 +48,10 @@ def test_linear_modules_and_incoherent_linear(qs, simt, bs):
     lin = make_linear(info, use_simt=simt)
     x = torch.randn(bs, K, device="cuda").half()
     y = lin(x).float().cpu().numpy()
-    ref = O.gemv_ref(W, x.cpu().numpy())
+    ref = R.h16(R.matvec(W, x.cpu().numpy()))  # `forward` returns inp.dtype (fp16) like the reference modules
     assert y.shape == (bs, M)
-    assert rel_l2(y, ref) <= 2e-3  # fp16 output rounding of the module API on top of the 1e-3 kernel budget
+    # the SIMT-layout kernels sum 4 products in fp16x2 before the fp32 accumulate (the reference accumulates in fp16 only)
+    assert rel_l2(y, ref) <= (2e-3 if simt else TOL)
     li = lin._info()  # `_info()` keeps the reference schema
     assert li["in_features"] == K and li["out_features"] == M and li["bias"] is None
     # left-only incoherent layer (as shipped: rot_info = skip_r)
@@ -56,8 +61,8 @@ def test_linear_modules_and_incoherent_linear(qs, simt, bs):
     layer = IncoherentLinear.gen_layer_from_info(info, merge_layers=True, use_simt=simt)
     if bs <= 8:
         out = layer(x).float().cpu().numpy()
-        ref2 = O.incoherent_linear_ref(x.cpu().numpy(), W, info["SU"].numpy(), info["Wscale"].numpy(), 32.0)
-        assert rel_l2(out, ref2) <= 3e-3
+        ref2 = R.incoherent_linear(x.cpu().numpy(), W, info["SU"].numpy(), info["Wscale"].numpy(), 32.0)
+        assert rel_l2(out, ref2) <= (2e-3 if simt else TOL)
 
 
 def test_merge_infos_equals_stacking():
@@ -99,104 +104,54 @@ def test_mlp_and_attention_modules():
     gate["linear_info"]["tlut"] = up["linear_info"]["tlut"]
     x = torch.randn(1, 1, H, device="cuda").half()
     Wu, Wg, Wd = decode_info(up["linear_info"]), decode_info(gate["linear_info"]), decode_info(down["linear_info"])
-    f = lambda t: t.float().cpu().numpy().astype(np.float64)
-    xs = f(x).reshape(-1)
-    z = O.hadamard_ref(xs * f(up["SU"])) / 64
-    u = (Wu.astype(np.float64) @ z) * f(up["Wscale"]) * 64
-    g = (Wg.astype(np.float64) @ z) * f(gate["Wscale"]) * 64
-    act = g / (1 + np.exp(-g)) * u
-    z2 = O.hadamard_ref(act * f(down["SU"])) / 64
-    ref = (Wd.astype(np.float64) @ z2) * f(down["Wscale"]) * 64
+    n16 = lambda t: t.cpu().numpy()
+    xs = n16(x).reshape(1, -1)
+    # reference graph with its fp16 rounding points (incoherent_linear.py:324-338)
+    u = R.incoherent_linear(xs, Wu, n16(up["SU"]), n16(up["Wscale"]), 64.0)
+    g = R.incoherent_linear(xs, Wg, n16(up["SU"]), n16(gate["Wscale"]), 64.0)  # up/gate share SU_ug
+    ref = R.incoherent_linear(R.silu_mul16(u, g), Wd, n16(down["SU"]), n16(down["Wscale"]), 64.0)
     for merge in (False, True):
         mlp = IncoherentMLP.gen_layer_from_info(cfg, up, gate, down, merge_ug=merge)
-        out = f(mlp(x)).reshape(-1)
-        assert rel_l2(out, ref) <= 1e-2, merge
-    # attention: merged qkv vs separate projections give the same result; cache grows
+        out = mlp(x).float().cpu().numpy().reshape(1, -1)
+        assert rel_l2(out, ref) <= TOL, merge
+    # attention against the oracle (incoherent_linear.py:76-203): every merge mode, three decode positions with a cache
     q, k, v, o = dress(mk("tcq_8_none_0.9", H, H), H, H), dress(mk("tcq_8_none_0.9", H, kvd), H, kvd), \
         dress(mk("tcq_8_none_0.9", H, kvd), H, kvd), dress(mk("tcq_8_none_0.9", H, H), H, H)
     for i in (k, v):
         i["linear_info"]["tlut"] = q["linear_info"]["tlut"]
-    outs = []
-    for merge in (dict(), dict(merge_qkv=True), dict(merge_kv=True)):
+    Wq, Wk, Wv, Wo = (decode_info(i["linear_info"]) for i in (q, k, v, o))
+    nh, nkv, D = 8, 2, 64
+    for merge in (dict(), dict(merge_qkv=True), dict(merge_kv=True), dict(merge_qk=True), dict(merge_qv=True)):
         attn = IncoherentSdpaAttention.gen_layer_from_info(cfg, 0, q, k, v, o, **merge)
         cache = StaticKVCache(1, 8, 2, 64)
-        ys = []
+        Kc, Vc = [], []
         for t in range(3):
             xt = torch.full((1, 1, H), 0.1 * (t + 1), device="cuda").half() + x
             y, _, _ = attn(xt, past_key_value=cache, cache_position=torch.tensor([t], device="cuda"))
-            ys.append(y)
-        outs.append(torch.cat(ys, 1))
-    assert torch.allclose(outs[0].float(), outs[1].float(), rtol=2e-2, atol=2e-3)
-    assert torch.allclose(outs[0].float(), outs[2].float(), rtol=2e-2, atol=2e-3)
-
-
-def _ref_layer_step(r, x_in_h, pos, caches):
-    """float64 restatement of one decode step of DecodeRunner (decoded weights from the oracle)."""
-    sh = r.shape
-    H, I = r.H, r.I
-    h = x_in_h.astype(np.float64)
-    D, nh, nkv = sh.head_dim, sh.num_attention_heads, sh.num_key_value_heads
-
-    def rms(v, w):
-        return v / np.sqrt((v * v).mean() + sh.rms_norm_eps) * w
-
-    t = lambda a: a.cpu().numpy()
-    f = lambda a: a.float().cpu().numpy().astype(np.float64)
-
-    def proj_W(p):
-        if getattr(p, "_Wref", None) is None:
-            p._Wref = proj_W_decode(p)
-        return p._Wref
-
-    def proj_W_decode(p):
-        if p.kind == "tcq_ldlq":
-            return O.tcq_decode(t(p.codes1), t(p.lut), p.M, p.K, p.KV1, p.S)
-        if p.kind == "combt_ldlq":
-            return O.tcq_decode_combt(t(p.codes1), t(p.codes2), t(p.lut), p.M, p.K, p.KV1, p.KV2, p.S)
-        if p.simt:
-            return O.simt_decode(t(p.codes1), t(p.lut), p.M, p.K, p.bits, p.vec)
-        return O.lut_tc_decode(t(p.codes1), t(p.lut), p.M, p.K, p.bits, p.vec)
-
-    for li, ly in enumerate(r.layers):
-        xin = rms(h, f(ly["norm1"]))
-        z = O.hadamard_ref(xin * f(ly["SU_qkv"])) / 64.0
-        acc = np.zeros(H + 2 * r.kvd)
-        for p, off in ly["qkv"]:
-            acc[off:off + p.M] = proj_W(p).astype(np.float64) @ z
-        qkv = acc * f(ly["W_qkv"]) * 64.0
-        q, k, v = qkv[:H].reshape(nh, D), qkv[H:H + r.kvd].reshape(nkv, D), qkv[H + r.kvd:].reshape(nkv, D)
-        ang = pos * r.inv_freq.double().cpu().numpy()
-        cos, sin = np.concatenate([np.cos(ang)] * 2), np.concatenate([np.sin(ang)] * 2)
-        rot = lambda a: np.concatenate([-a[..., D // 2:], a[..., :D // 2]], -1)
-        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
-        caches[li][0].append(k)
-        caches[li][1].append(v)
-        Kc, Vc = np.stack(caches[li][0], 0), np.stack(caches[li][1], 0)  # (T, nkv, D)
-        out = np.zeros((nh, D))
-        for hd in range(nh):
-            kv = hd // (nh // nkv)
-            s = Kc[:, kv] @ q[hd] / math.sqrt(D)
-            pm = np.exp(s - s.max())
-            pm /= pm.sum()
-            out[hd] = pm @ Vc[:, kv]
-        z = O.hadamard_ref(out.reshape(-1) * f(ly["SU_o"])) / 64.0
-        h = h + (proj_W(ly["o"]).astype(np.float64) @ z) * f(ly["W_o"]) * 64.0
-        xin = rms(h, f(ly["norm2"]))
-        z = O.hadamard_ref(xin * f(ly["SU_ug"])) / 64.0
-        acc = np.zeros(2 * I)
-        for p, off in ly["ug"]:
-            acc[off:off + p.M] = proj_W(p).astype(np.float64) @ z
-        ug = acc * f(ly["W_ug"]) * 64.0
-        up, gate = ug[:I], ug[I:]
-        act = gate / (1 + np.exp(-gate)) * up
-        z = O.hadamard_ref(act * f(ly["SU_dp"])) / 64.0
-        h = h + (proj_W(ly["down"]).astype(np.float64) @ z) * f(ly["W_dp"]) * 64.0
-    xf = rms(h, f(r.final_norm))
-    return h, f(r.lm_head) @ xf
+            xs = n16(xt).reshape(1, -1)
+            # q/k/v projections share SU_qkv (= info_q's SU); the module's own compute_qkv is checked at TOL
+            su = n16(q["SU"])
+            qr = R.incoherent_linear(xs, Wq, su, n16(q["Wscale"]), 64.0)
+            kr = R.incoherent_linear(xs, Wk, su, n16(k["Wscale"]), 64.0)
+            vr = R.incoherent_linear(xs, Wv, su, n16(v["Wscale"]), 64.0)
+            mq, mk_, mv = attn.compute_qkv(xt)
+            assert rel_l2(mq.float().cpu().numpy().reshape(1, -1), qr) <= TOL
+            assert rel_l2(mk_.float().cpu().numpy().reshape(1, -1), kr) <= TOL
+            assert rel_l2(mv.float().cpu().numpy().reshape(1, -1), vr) <= TOL
+            inv = attn.inv_freq.cpu().numpy()
+            Kc.append(R.rope16(kr.reshape(nkv, D), t, inv, fused=False))
+            Vc.append(vr.reshape(nkv, D))
+            a = R.attend(R.rope16(qr.reshape(nh, D), t, inv, fused=False), np.stack(Kc), np.stack(Vc), nh // nkv)
+            ref_o = R.incoherent_linear(a.reshape(1, -1), Wo, n16(o["SU"]), n16(o["Wscale"]), 64.0)
+            co = attn.compute_o(torch.from_numpy(a.reshape(1, 1, -1)).cuda())
+            assert rel_l2(co.float().cpu().numpy().reshape(1, -1), ref_o) <= TOL
+            # whole forward: torch's SDPA backend decides the rounding of scores / probabilities inside (as in the reference)
+            assert rel_l2(y.float().cpu().numpy().reshape(1, -1), ref_o) <= 2e-3, (merge, t)
 
 
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged", "uniform_merged_grid_silu", "uniform_merged_d128"])
+@pytest.mark.parametrize("variant", ["uniform_merged", "mixed_unmerged", "uniform_merged_grid_silu", "uniform_merged_d128",
+                                     "merge_qv_qk"])
 def test_decode_step_matches_restatement(variant, fused):
     from qpalette.decode import DecodeRunner, LlamaShape, uniform_qdict
     # intermediate 4096 = 8 * 512 takes the multi-CTA SiLU*mul/Hadamard kernel in the fused list, 28 * 128 the single-CTA one;
@@ -205,7 +160,9 @@ def test_decode_step_matches_restatement(variant, fused):
     heads = 4 if variant == "uniform_merged_d128" else 8
     shape = LlamaShape(hidden_size=512, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=heads,
                        num_key_value_heads=2, vocab_size=1024)
-    if variant.startswith("uniform_merged"):
+    if variant == "merge_qv_qk":  # the two remaining attention merges of the reference's merge_info vocabulary
+        qd, mi = uniform_qdict(shape, "tcq_7_none_0.9"), [["merge_qv", "merge_ug"], ["merge_qk"]]
+    elif variant.startswith("uniform_merged"):
         qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 2
     else:
         qd = uniform_qdict(shape, "tcq_8_none_0.9")
@@ -221,15 +178,17 @@ def test_decode_step_matches_restatement(variant, fused):
     tok = 5
     r.reset(tok)
     for step in range(70 if long_ctx else 3):
-        x0 = r.embed[tok].float().cpu().numpy()
-        _, logits_ref = _ref_layer_step(r, x0, step, caches)
+        _, logits_ref = R.decode_step_ref(r, r.embed[tok].cpu().numpy(), step, caches)
         r.step()
         torch.cuda.synchronize()
         logits = r.logits.cpu().numpy()
-        assert rel_l2(logits, logits_ref) <= 2e-2, (variant, step)  # fp16 residual stream vs float64 restatement
+        # restatement with the graph's fp16 rounding points; the mixed variant has SIMT-layout projections (fp16x2 partial sums)
+        assert rel_l2(logits, logits_ref) <= (2e-3 if variant == "mixed_unmerged" else TOL), (variant, step)
         assert int(r.pos.item()) == step + 1
         tok = int(r.token.item())
         assert tok == int(np.argmax(logits))
+    with pytest.raises(RuntimeError):  # the KV cache holds max_seq rows: stepping past it is refused, not written out of bounds
+        r.generate(r.max_seq + 1)
     eager = r.generate(4, token=7)  # graph replay reproduces the eager tokens
     r.capture()
     assert r.generate(4, token=7) == eager
@@ -309,4 +268,4 @@ def test_figure1d_layers_fused_vs_unfused():
         torch.cuda.empty_cache()
     for a, b in zip(*logits):
         assert np.isfinite(a).all() and np.isfinite(b).all()
-        assert rel_l2(a, b) <= 2e-2
+        assert rel_l2(a, b) <= TOL  # same rounding points, different launch lists
