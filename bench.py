@@ -47,15 +47,49 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (the timed region of
+    the default run is ~40 ms, shorter than nvidia-smi's smallest useful period); falls back to `nvidia-smi -lms` if
+    nvidia_ml_py cannot be used."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+
+    def _poll(self):
+        import pynvml as N
+        h = self.nvml
+        bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                try:
+                    r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.nvml = N.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.nvml, N.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -69,6 +103,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -85,7 +124,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -149,28 +188,89 @@ def cpu_tokens_per_s(sample_s, sample_weights):
     return 1.0 / (sample_s / sample_weights * QUANT_WEIGHTS_PER_TOKEN + cpu_lm_head_seconds())
 
 
+def bench_config(workload, quantizer, parallelism, layers, weight_gb, max_seq):
+    """the `config` dict both arms print (the driver compares them key by key)"""
+    return {"workload": workload, "quantizer": quantizer, "parallelism": parallelism, "layers": layers,
+            "l2_policy": f"inputs larger than L2: {weight_gb:.1f} GB of weights streamed per step, no reuse between steps",
+            "max_seq": max_seq}
+
+
 def run_reference(args):
+    """CPU arm: the reference's dequantize -> matvec path (restated in C, oracle/qp_cref.c: the reference's CUDA extensions
+    do not build here and its python stack does not import) on all host threads.  One step = a bounded
+    sample of a token's work: the q_proj (4096x4096, BASELINE configs[0]) and the down_proj (4096x14336) of one layer, i.e.
+    1/92 of a token's quantized weights, extrapolated to a token by weight count; the fp16 lm_head matvec is timed apart."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    M, K = 4096, 4096  # BASELINE.json configs[0]: one q_proj-shaped tcomb_6_7 layer per step
     times = []
     threads = 1
     for i in range(args.warmup + args.steps):
-        t, threads = cpu_sample_seconds(M, K)
+        t_q, threads = cpu_sample_seconds(4096, 4096)
+        t_d, _ = cpu_sample_seconds(4096, 14336)
         if i >= args.warmup:
-            times.append(t)
+            times.append(t_q + t_d)
     avg = sum(times) / len(times)
-    v = cpu_tokens_per_s(avg, M * K)
-    sample = f"per step: one 4096x4096 {QUANTIZER} dequantize+matvec (configs[0]) in C on {threads} threads; extrapolated to a token"
+    w = 4096 * 4096 + 4096 * 14336
+    v = cpu_tokens_per_s(avg, w)
+    W = max(args.warmup, 3)
+    max_seq = max(64, W + args.steps * 2 + 16)
+    weight_gb = (QUANT_WEIGHTS_PER_TOKEN * 3.25 / 8 + LM_HEAD_WEIGHTS * 2) / 1e9
+    sample = (f"per step: q_proj 4096x4096 + down_proj 4096x14336 of {QUANTIZER} (1/92 of a token's quantized weights), C port of "
+              f"the reference's dequantize->matvec on {threads} threads; extrapolated to a token by weight count + fp16 lm_head")
+    extra = {}
+    if os.path.isdir("/root/reference"):  # build container only: the reference's own torch decode for the even-KV half
+        extra["torch_decode_compressed"] = "see BASELINE.md section 3 (timed in the build container)"
     print(json.dumps({
         "impl": "reference", "metric": "decode_tok_per_s", "value": v, "unit": "tok/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": avg * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "quantizer": QUANTIZER},
+        "config": bench_config(WORKLOAD, QUANTIZER, f"replicas{args.gpus}", 32, weight_gb, max_seq),
         "cpu_baseline": {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def measure_tp70b(world, rank, pg, steps, warmup):
+    """BASELINE.json configs[4]: Llama-3.1-70B-shaped TCQ-3.25 decode with every layer row-sharded over the `world` GPUs
+    (north_star).  Returns the dict printed under `extra.tp70b`."""
+    import torch
+    import torch.distributed as dist
+    from qpalette.decode import LLAMA31_70B, DecodeRunner, uniform_qdict
+    shape = LLAMA31_70B
+    qd, mi = uniform_qdict(shape, QUANTIZER), [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers
+    max_seq = max(64, warmup + steps * 2 + 16)
+    r = DecodeRunner(shape, qd, mi, max_seq=max_seq, seed=0, rank=rank, world=world, process_group=pg if world > 1 else None)
+    r.capture()
+    stream = torch.cuda.current_stream()
+    r.reset(1)
+    for _ in range(warmup):
+        r.step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        r.step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = {"workload": "Llama-3.1-70B-shaped bs=1 decode, uniform TCQ-3.25, rows of every layer sharded over the GPUs",
+           "n_gpus": world, "tok_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "launches_per_step": r.launches_per_step,
+           "exchanges_per_step": 4 * r.L if world > 1 else 0,
+           "exchange": ("NVLink peer stores fused into the consumer kernels" if r.p2p else "ncclAllGather") if world > 1 else None,
+           "weight_bytes_per_gpu": r.weight_bytes + r.lm_head_bytes, "scaling": "strong"}
+    out["per_gpu_GBps"] = out["weight_bytes_per_gpu"] * out["tok_s"] / 1e9
+    del r
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -187,6 +287,8 @@ def main():
                          "MSQ qdict + merge_info for Llama-3.1-8B (configs/*.json, BASELINE.json configs[2])")
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (invalid as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tp-extra", action="store_true",
+                    help="skip the additional row-sharded 70B-shaped measurement printed under extra.tp70b")
     ap.add_argument("--unfused", action="store_true",
                     help="debug: separate RMSNorm/Hadamard launches instead of the fused GEMV prologues (9 launches per layer)")
     args = ap.parse_args()
@@ -307,15 +409,17 @@ def main():
         os_ = [ly["o"] for ly in runner.layers]                      # 4096 x 4096
         alg = lambda p: p.weight_bytes + 2 * p.K + 4 * p.M + 2048    # codes + x (fp16) + out (fp32) + tlut
         t_down = time_proj(downs, runner.x_i, runner.acc_dn)
-        traffic = None
+        # DRAM traffic per launch cannot be measured without ncu: it is quoted from the committed capture (and says so)
+        traffic, traffic_source = None, None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
-            traffic = prof.get("tcq_gemv_4096x14336_tcomb_6_7", {}).get("dram_bytes_per_launch")
+            ent = prof.get("tcq_gemv_4096x14336_tcomb_6_7", {})
+            traffic, traffic_source = ent.get("dram_bytes_per_launch"), "not measured in this run: " + ent.get("source", "profiles/summary.json")
         except Exception:
             pass
         ach = alg(downs[0]) / t_down / 1e9
         roofline = {"bound": "hbm", "kernel": "tcq_gemv_kernel<6,7,9> 4096x14336 (down_proj)", "achieved": ach, "peak": peak,
-                    "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_source,
                     "algorithmic_bytes": alg(downs[0]), "us_per_launch": t_down * 1e6}
         for name, projs, x, out in (("ug_28672x4096", ugs, runner.x_h, runner.acc_ug), ("qkv_6144x4096", qkvs, runner.x_h, runner.acc_qkv),
                                     ("o_4096x4096", os_, runner.x_h, runner.acc_o)):
@@ -337,20 +441,27 @@ def main():
         except Exception as ex:  # the checker library is test infrastructure; a missing one must not hide the GPU number
             cpu = {"value": None, "unit": "tok/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
 
+    # ---- row-sharded 70B-shaped decode (BASELINE configs[4]) measured in the same run: every rank takes part --------------
+    runner_L, bytes_per_token = runner.L, runner.bytes_per_token()
+    extra = {}
+    if args.workload == "8b" and args.parallel == "replicas" and not args.no_tp_extra and args.layers is None:
+        del runner
+        torch.cuda.empty_cache()
+        try:
+            extra["tp70b"] = measure_tp70b(world, rank, pg, min(args.steps, 20), 3)
+        except Exception as ex:  # must not hide the headline number
+            extra["tp70b"] = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         line = {
             "metric": "decode_tok_per_s", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.parallel == "tp" else "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": wl_name,
-                       "quantizer": q_name, "parallelism": f"{args.parallel}{world}", "layers": runner.L,
-                       "l2_policy": f"inputs larger than L2: {runner.bytes_per_token() / 1e9:.1f} GB of weights streamed per step, "
-                                    "no reuse between steps",
-                       "max_seq": max_seq},
+            "config": bench_config(wl_name, q_name, f"{args.parallel}{world}", runner_L, bytes_per_token / 1e9, max_seq),
             "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_detail": detail,
-            "cpu_baseline": cpu, "lib": os.path.basename(_cabi.LIB_PATH),
+            "cpu_baseline": cpu, "extra": extra, "lib": os.path.basename(_cabi.LIB_PATH),
         }
         print(json.dumps(line))
     if world > 1:

@@ -11,6 +11,8 @@
 //   qp_argmax, qp_embed, qp_step_advance : sampling / embedding / device-side position counter so a whole decode step is
 //                       one CUDA graph that is replayed per token.
 // Single-CTA kernels here are latency-bound by design (a few KB of data); they exist to remove launches.
+// Every buffer that another kernel of the same decode step writes (h, the fp32 accumulators, attention output, x, logits, token,
+// position) is read with ld.global.cg (__ldcg): kernels overlap under programmatic dependent launch and the L1 is not coherent.
 #include "had_common.cuh"
 
 namespace qp {
@@ -179,8 +181,8 @@ fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, co
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * kDecThreads;
         const bool ok = c < nch;
-        hv[j] = ok ? reinterpret_cast<const uint2 *>(h)[c] : make_uint2(0u, 0u);
-        av[j] = (ok && acc) ? reinterpret_cast<const float4 *>(acc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[j] = ok ? __ldcg(reinterpret_cast<const uint2 *>(h) + c) : make_uint2(0u, 0u);
+        av[j] = (ok && acc) ? __ldcg(reinterpret_cast<const float4 *>(acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (zero_ptr) zero_words4(zero_ptr, zero_count);
     const __half hs = __float2half(acc_scale);
@@ -263,8 +265,8 @@ silu_mul_had_kernel(__half *__restrict__ x_out, const float *__restrict__ acc, c
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * kDecThreads;
         const bool ok = c < nch;
-        au[j] = ok ? reinterpret_cast<const float4 *>(acc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        ag[j] = ok ? reinterpret_cast<const float4 *>(acc + I)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        au[j] = ok ? __ldcg(reinterpret_cast<const float4 *>(acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ag[j] = ok ? __ldcg(reinterpret_cast<const float4 *>(acc + I) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         wu[j] = ok ? reinterpret_cast<const uint2 *>(wscale)[c] : make_uint2(0u, 0u);
         wg[j] = ok ? reinterpret_cast<const uint2 *>(wscale + I)[c] : make_uint2(0u, 0u);
         sv[j] = (ok && su) ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
@@ -326,8 +328,8 @@ silu_mul_had_grid_kernel(__half *__restrict__ x_out, float *acc, const __half *_
     const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
     pdl_wait();
     pdl_launch_dependents();
-    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
-    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
+    const float4 au = __ldcg(reinterpret_cast<const float4 *>(acc) + c);
+    const float4 ag = __ldcg(reinterpret_cast<const float4 *>(acc + I) + c);
     if (zero_ptr) {  // this CTA's slice of the accumulators to clear for later launches
         const int per = ((zero_count + NB - 1) / NB + 3) & ~3;
         const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
@@ -426,8 +428,8 @@ silu_mul_had_cluster_kernel(__half *__restrict__ x_out, const float *__restrict_
     const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[c] : make_uint2(0u, 0u);
     pdl_wait();
     pdl_launch_dependents();
-    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
-    const float4 ag = reinterpret_cast<const float4 *>(acc + I)[c];
+    const float4 au = __ldcg(reinterpret_cast<const float4 *>(acc) + c);
+    const float4 ag = __ldcg(reinterpret_cast<const float4 *>(acc + I) + c);
     if (zero_ptr) {
         const int per = ((zero_count + CL - 1) / CL + 3) & ~3;
         const int lo = min(b * per, zero_count), hi = min(lo + per, zero_count);
@@ -518,8 +520,8 @@ silu_mul_had_grid_xchg_kernel(__half *__restrict__ x_out, const float *__restric
     const int gb = xc.rank * nbl + b;          // global block
     const int c = b * kSiluThreads + t;        // local chunk of 4 consecutive elements
     const unsigned ep = *xc.epoch + 1u;        // every CTA reads it before any CTA can get past the barrier below
-    const float4 au = reinterpret_cast<const float4 *>(acc)[c];
-    const float4 ag = reinterpret_cast<const float4 *>(acc + Il)[c];
+    const float4 au = __ldcg(reinterpret_cast<const float4 *>(acc) + c);
+    const float4 ag = __ldcg(reinterpret_cast<const float4 *>(acc + Il) + c);
     const uint2 wu = reinterpret_cast<const uint2 *>(wscale)[c];
     const uint2 wg = reinterpret_cast<const uint2 *>(wscale + Il)[c];
     const uint2 sv = su ? reinterpret_cast<const uint2 *>(su)[gb * kSiluThreads + t] : make_uint2(0u, 0u);
@@ -633,15 +635,15 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     // costs one memory round trip that overlaps the q/k/v epilogue + RoPE below.
     // a position past the cache capacity would write out of bounds (cache rows and the score array hold max_seq entries):
     // clamp to the last row -- the host API refuses to step that far (DecodeRunner.step), this only keeps memory safe
-    const int pos = min(*pos_ptr, max_seq - 1);
+    const int pos = min(__ldcg(pos_ptr), max_seq - 1);
     uint2 kpre[8], vpre[8];
     if (D == 128) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int t = warp + u * nw;
             const size_t row = ((size_t)t * Hkv + kvh) * D;
-            kpre[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + row)[lane] : make_uint2(0u, 0u);
-            vpre[u] = (t < pos) ? reinterpret_cast<const uint2 *>(vcache + row)[lane] : make_uint2(0u, 0u);
+            kpre[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(kcache + row) + lane) : make_uint2(0u, 0u);
+            vpre[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(vcache + row) + lane) : make_uint2(0u, 0u);
         }
     }
     // likewise independent of the preceding kernel: the per-row scales and the rotary angle of this position
@@ -666,7 +668,8 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     const __half hs = __float2half(acc_scale);
     if (d < D) {
         // all loads first
-        const float aq = acc_qkv[iq + d], aqp = acc_qkv[iq + pd], ak = acc_qkv[ik + d], akp = acc_qkv[ik + pd], av = acc_qkv[iv + d];
+        const float aq = __ldcg(acc_qkv + iq + d), aqp = __ldcg(acc_qkv + iq + pd), ak = __ldcg(acc_qkv + ik + d),
+                    akp = __ldcg(acc_qkv + ik + pd), av = __ldcg(acc_qkv + iv + d);
         const float sgn = d < half ? -1.f : 1.f;
         const float qa = scaled_acc(aq, wq, hs), qb = scaled_acc(aqp, wqp, hs);
         const float ka = scaled_acc(ak, wk, hs), kb = scaled_acc(akp, wkp, hs);
@@ -691,7 +694,7 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
             for (int u = 0; u < 8; ++u) {
                 const int t = t0 + u * nw;
                 if (t0 == warp) kv[u] = kpre[u];  // first batch: prefetched
-                else kv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
+                else kv[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D) + lane) : make_uint2(0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -708,7 +711,7 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
         for (int t = warp; t < pos; t += nw) {
             const __half *kr = kcache + ((size_t)t * Hkv + kvh) * D;
             float s = 0.f;
-            for (int i = lane; i < D; i += 32) s += q[i] * __half2float(kr[i]);
+            for (int i = lane; i < D; i += 32) s += q[i] * __half2float(__ldcg(kr + i));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) sc[t] = s * scale;
@@ -743,7 +746,7 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
             for (int u = 0; u < 8; ++u) {
                 const int t = t0 + u * nw;
                 if (t0 == warp) vv[u] = vpre[u];
-                else vv[u] = (t < pos) ? reinterpret_cast<const uint2 *>(vcache + ((size_t)t * Hkv + kvh) * D)[lane] : make_uint2(0u, 0u);
+                else vv[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(vcache + ((size_t)t * Hkv + kvh) * D) + lane) : make_uint2(0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -776,7 +779,7 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int t = t0 + u * nparts;
-                vv[u] = (t < pos) ? vcache[((size_t)t * Hkv + kvh) * D + dd] : __float2half(0.f);
+                vv[u] = (t < pos) ? __ldcg(vcache + ((size_t)t * Hkv + kvh) * D + dd) : __float2half(0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -803,7 +806,7 @@ gemv_f16_kernel(float *__restrict__ out, const __half *__restrict__ W, const __h
     pdl_wait();
     pdl_launch_dependents();
     const int kq = K / 8;
-    for (int i = threadIdx.x; i < kq; i += blockDim.x) xs[i] = reinterpret_cast<const uint4 *>(x)[i];
+    for (int i = threadIdx.x; i < kq; i += blockDim.x) xs[i] = __ldcg(reinterpret_cast<const uint4 *>(x) + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
@@ -850,7 +853,7 @@ __global__ void argmax_kernel(int *__restrict__ token_out, const float *__restri
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float v = logits[i];
+        const float v = __ldcg(logits + i);
         if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
     }
     auto reduce = [&](float &v, int &ix) {
@@ -897,7 +900,7 @@ __global__ void argmax_kernel(int *__restrict__ token_out, const float *__restri
 __global__ void embed_kernel(__half *__restrict__ h, const __half *__restrict__ table, const int *__restrict__ token, int n) {
     pdl_wait();
     pdl_launch_dependents();
-    const size_t row = (size_t)(*token);
+    const size_t row = (size_t)__ldcg(token);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) h[i] = table[row * n + i];
 }
 

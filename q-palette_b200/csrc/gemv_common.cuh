@@ -36,6 +36,8 @@ __device__ __forceinline__ void pack_load_raw(uint32_t (&raw)[TcqGeom<E>::kRawWo
 
 // cooperative global -> shared copy of n 32-bit words; every thread issues all of its loads before its stores so the
 // L2 round trips overlap instead of serialising (this prologue sits on the critical path of a ~5 us kernel)
+// kCoherent: the source is an activation written by another kernel of the same step -> ld.global.cg (L2), see stage_x
+template <bool kCoherent = false>
 __device__ __forceinline__ void coop_copy_words(uint32_t *dst, const uint32_t *__restrict__ src, int n) {
     constexpr int U = 8;
     for (int base = threadIdx.x; base < n; base += U * blockDim.x) {
@@ -43,7 +45,7 @@ __device__ __forceinline__ void coop_copy_words(uint32_t *dst, const uint32_t *_
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * blockDim.x;
-            v[u] = (i < n) ? __ldg(src + i) : 0u;
+            v[u] = (i < n) ? (kCoherent ? __ldcg(src + i) : __ldg(src + i)) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -56,7 +58,10 @@ __device__ __forceinline__ void coop_copy_words(uint32_t *dst, const uint32_t *_
 // stage x (bs, K) fp16 into shared memory in B-fragment order: 16 bytes per (super-tile column kh, batch row n, q):
 // {x[n][k0+2q..+1], x[n][k0+8+2q..+1], x[n][k0+16+2q..+1], x[n][k0+24+2q..+1]},  k0 = 32*kh.
 // Each thread pulls up to 4 x 16 bytes into registers with all loads in flight together (one L2 round trip per round:
-// a single round for bs*K <= 24576), then scatters the words.
+// a single round for bs*K <= 24576), then scatters the words (4-way bank-conflicted 32-bit stores: measured cheaper than a
+// conflict-free store fed by a 4-byte gather, whose 25 % sector efficiency costs more L1 request cycles than it saves).
+// x is produced by the preceding kernel, which may still overlap this one's prologue (programmatic dependent launch): it is
+// read at L2 (ld.global.cg), not through the non-coherent L1 path.
 __device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict__ x32, int K, int bs) {
     const int kq = K / 8;            // uint4 per batch row
     const int total = bs * kq;       // uint4 to move
@@ -67,7 +72,7 @@ __device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * blockDim.x;
-            v[u] = (i < total) ? __ldg(x4 + i) : make_uint4(0u, 0u, 0u, 0u);
+            v[u] = (i < total) ? __ldcg(x4 + i) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -367,6 +372,289 @@ __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __hal
             }
         }
     }
+}
+
+// =====================================================================================================================
+// v2 streaming skeleton (round 2).  Same data path as above -- per-lane streaming loads into a register ring, decode,
+// mma.m16n8k16 against x fragments in shared memory, fp32 atomics per finished strip -- but organised for the fewest issued
+// instructions per super-tile and a small instruction footprint (the round-1 loop spent ~35 of its 155 warp-instructions
+// per super-tile on strip / x-address bookkeeping and was 100 KB of SASS per instantiation):
+//   * every WARP owns one contiguous run of super-tiles (a CTA's 24 runs are adjacent, so the CTA still streams one
+//     contiguous byte range): the column index advances by one per step, the x-fragment address by a constant, and the
+//     strip changes at most once every `ksuper` steps (counted down in a uniform register);
+//   * one main loop whose D unrolled steps are all valid, one predicated tail of < D steps; the flush is out of line.
+// =====================================================================================================================
+#ifndef QP_GEMV2_DEPTH
+#define QP_GEMV2_DEPTH 3
+#endif
+constexpr int kGemv2Depth = QP_GEMV2_DEPTH;
+
+struct WarpRun2 {
+    unsigned lo;  // first super-tile (flat [strip][column] index inside the part)
+    int n;        // super-tiles of this warp
+    int mh, kh;   // strip / column of the first one
+};
+__device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSplit split, int gwarp) {
+    unsigned lo, hi;
+    split_range(split, gwarp, lo, hi);
+    WarpRun2 r;
+    r.lo = lo;
+    r.n = (int)(hi - lo);
+    r.mh = (int)(lo / (unsigned)seg.ksuper);
+    r.kh = (int)(lo - (unsigned)r.mh * (unsigned)seg.ksuper);
+    return r;
+}
+
+template <int E>
+__device__ __forceinline__ const uint32_t *gemv2_lane_ptr(const PackSegment seg, const WarpRun2 run) {
+    int word0, bitoff;
+    tcq_lane_addr<E>(threadIdx.x & 31, word0, bitoff);
+    return seg.codes + word0 + (size_t)run.lo * (TcqGeom<E>::kSuperBytes / 4);
+}
+
+// issue the first D payload loads of this warp's run
+template <int E>
+__device__ __forceinline__ void gemv2_prefetch(const PackSegment seg, const WarpRun2 run,
+                                               uint32_t (&raw)[kGemv2Depth][TcqGeom<E>::kRawWords]) {
+    using G = TcqGeom<E>;
+    const uint32_t *p = gemv2_lane_ptr<E>(seg, run);
+#pragma unroll
+    for (int d = 0; d < kGemv2Depth; ++d) {
+#pragma unroll
+        for (int i = 0; i < G::kRawWords; ++i) raw[d][i] = 0u;
+        pack_load_raw_pred<E>(raw[d], p + d * (G::kSuperBytes / 4), d < run.n);
+    }
+}
+
+// add the C fragments of a finished 32-row strip to out (bs, M) and clear them: lane l holds rows row + l/4 + {0, 8, 16, 24}
+// of batch columns 2(l%4) and 2(l%4) + 1.  Everything it needs is recomputed here from kernel parameters: the strip changes
+// once every `ksuper` steps, so nothing of this may stay live in (or be rematerialised into) the streaming loop.
+__device__ __forceinline__ void gemv2_flush(float *__restrict__ out, int M, int bs, int row, float (&acc)[2][4]) {
+    const int lane = threadIdx.x & 31;
+    const int c0 = 2 * (lane & 3);
+    float *a = out + (size_t)c0 * M + row + (lane >> 2);
+    if (c0 < bs) {
+        atomicAdd(a, acc[0][0]);
+        atomicAdd(a + 8, acc[0][2]);
+        atomicAdd(a + 16, acc[1][0]);
+        atomicAdd(a + 24, acc[1][2]);
+    }
+    if (c0 + 1 < bs) {
+        a += M;
+        atomicAdd(a, acc[0][1]);
+        atomicAdd(a + 8, acc[0][3]);
+        atomicAdd(a + 16, acc[1][1]);
+        atomicAdd(a + 24, acc[1][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// shared-memory address of a lane's x fragment for column 0 of a part (see stage_x): a lane past the batch reads row 0's
+// fragment -- its mma columns are never stored, so no zero-fill and no predicate is needed
+__device__ __forceinline__ uint32_t gemv2_xbase(uint32_t xs_addr, int ksuper0, int bs) {
+    const int lane = threadIdx.x & 31, nq = lane >> 2, q = lane & 3;
+    return xs_addr + ((uint32_t)ksuper0 * (uint32_t)bs + (uint32_t)(nq < bs ? nq : 0)) * 64u + (uint32_t)q * 16u;
+}
+
+// one super-tile: payload registers -> decode -> 4 mma
+template <class Dec>
+__device__ __forceinline__ void gemv2_consume(const uint32_t (&P)[TcqGeom<Dec::kE>::kWords], uint32_t xaddr, int lane,
+                                              uint32_t tab_lane, float (&acc)[2][4]) {
+    const uint4 xb = lds_u128(xaddr);
+    uint32_t frag[4][4];  // [tile = kl*2+ml][register]
+    Dec::decode(P, lane, tab_lane, frag);
+    mma_16816(acc[0], frag[0][0], frag[0][1], frag[0][2], frag[0][3], xb.x, xb.y);
+    mma_16816(acc[1], frag[1][0], frag[1][1], frag[1][2], frag[1][3], xb.x, xb.y);
+    mma_16816(acc[0], frag[2][0], frag[2][1], frag[2][2], frag[2][3], xb.z, xb.w);
+    mma_16816(acc[1], frag[3][0], frag[3][1], frag[3][2], frag[3][3], xb.z, xb.w);
+}
+
+// stream this warp's run of one part.  xs_addr = shared-memory address of the staged x (fragment order, see stage_x);
+// `between` runs once after the main loop, before the tail (used to issue the next part's first loads).
+template <class Dec, class Between>
+__device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restrict__ out, int M, int bs, uint32_t xs_addr,
+                                          uint32_t tab_lane, const WarpRun2 run,
+                                          uint32_t (&raw)[kGemv2Depth][TcqGeom<Dec::kE>::kRawWords], Between between) {
+    constexpr int E = Dec::kE, D = kGemv2Depth;
+    using G = TcqGeom<E>;
+    constexpr int SBw = G::kSuperBytes / 4;  // words per super-tile
+    const int lane = threadIdx.x & 31;
+    const int bitoff = (lane * G::kLaneBytes & 3) * 8;
+    const uint32_t xstep = (uint32_t)bs * 64u;
+    uint32_t xa = gemv2_xbase(xs_addr, seg.ksuper0, bs) + (uint32_t)run.kh * xstep;
+    int row = seg.row0 + run.mh * 32;
+    int kleft = seg.ksuper - run.kh;  // steps until the strip ends (warp-uniform)
+
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const uint32_t *p = gemv2_lane_ptr<E>(seg, run) + D * SBw;  // refill source of ring slot 0
+    const int n = run.n;
+    int i = 0;
+    auto advance = [&]() {
+        xa += xstep;
+        if (--kleft == 0) {  // rare: once per strip
+            gemv2_flush(out, M, bs, row, acc);
+            row += 32;
+            kleft = seg.ksuper;
+            xa = gemv2_xbase(xs_addr, seg.ksuper0, bs);
+        }
+    };
+    // main loop: D valid steps per trip; a refill is predicated on its super-tile being inside the run
+    for (; i + D <= n; i += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            uint32_t P[G::kWords];
+            tcq_align<E>(raw[d], bitoff, P);  // the slot's registers are dead after this: the refill lands in them
+            pack_load_raw_pred<E>(raw[d], p + d * SBw, i + d + D < n);
+            gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+            advance();
+        }
+        p += D * SBw;
+    }
+    between();
+    // tail: n - i < D steps left, already in the ring
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) {
+        if (i + d < n) {
+            uint32_t P[G::kWords];
+            tcq_align<E>(raw[d], bitoff, P);
+            gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+            advance();
+        }
+    }
+    if (n > 0 && kleft != seg.ksuper) gemv2_flush(out, M, bs, row, acc);
+}
+
+// =====================================================================================================================
+// v3: the packed codes reach the decode through a per-warp SHARED-MEMORY RING filled by 16-byte asynchronous copies
+// (cp.async.cg, LDGSTS) instead of per-lane ld.global into registers.  Why (measured, tools/ubench_mio.cu on B200): a warp's
+// per-lane 32-bit loads at a 12 / 14-byte lane stride cost 4.8 SM-cycles of L1 request bandwidth EACH -- every one of the 3-4
+// loads of a super-tile touches all of its 12-14 sectors, 3-4x the useful sector requests -- i.e. 15-21 of the ~27 cycles a
+// super-tile may cost per SM, while one fully coalesced 16-byte-per-lane copy of the same 384-448 bytes costs ~6 and a
+// lane-replicated LDS.32 gather 0.27.  The ring is private to a warp (no cross-warp synchronisation): kRingDepth slots of one
+// super-tile, one cp.async group per slot; a step waits for the oldest group, reads its payload with 3-4 LDS.32 (any lane
+// alignment: the slot is a flat copy of the super-tile), decodes, and refills the slot with the super-tile kRingDepth ahead.
+// (A 1-D bulk copy -- cp.async.bulk + mbarrier, zero LSU cost -- was built first: its uniform-register operands cost ptxas an
+// elect-one loop and 5-7 R2UR per copy, ~25 issue slots per super-tile against ~10 here; the loop is issue-bound next.)
+// =====================================================================================================================
+#ifndef QP_RING_DEPTH
+#define QP_RING_DEPTH 4
+#endif
+constexpr int kRingDepth = QP_RING_DEPTH;
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred, uint64_t policy) {
+    (void)policy;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst),
+        "l"(src), "r"((int)pred)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// the stream of super-tiles a warp will consume: its run of part A followed by its run of part B (rem2 = 0: single part).
+// src already includes this lane's 16-byte column (lane * 16); `lane_ok` = this lane's column lies inside the super-tile.
+struct RingFeed {
+    const uint8_t *src;   // next super-tile to fetch (+ lane * 16)
+    int rem;              // super-tiles of the current part still to fetch
+    uint32_t bytes;       // bytes per super-tile of the current part
+    bool lane_ok;
+    const uint8_t *src2;  // the following part
+    int rem2;
+    uint32_t bytes2;
+};
+__device__ __forceinline__ RingFeed make_feed(const void *a, size_t lo_a, int n_a, int bytes_a, const void *b, size_t lo_b, int n_b,
+                                              int bytes_b) {
+    const uint32_t l16 = (threadIdx.x & 31) * 16u;
+    RingFeed f;
+    f.src = reinterpret_cast<const uint8_t *>(a) + lo_a * (size_t)bytes_a + l16;
+    f.rem = n_a, f.bytes = (uint32_t)bytes_a, f.lane_ok = l16 < (uint32_t)bytes_a;
+    f.src2 = b ? reinterpret_cast<const uint8_t *>(b) + lo_b * (size_t)bytes_b + l16 : nullptr;
+    f.rem2 = b ? n_b : 0, f.bytes2 = (uint32_t)bytes_b;
+    if (f.rem == 0 && f.rem2 != 0) {
+        f.src = f.src2, f.rem = f.rem2, f.bytes = f.bytes2, f.rem2 = 0;
+        f.lane_ok = l16 < f.bytes;
+    }
+    return f;
+}
+// start the copy of the next super-tile of the feed into `slot_lane` (= slot address + lane * 16) and close its group (an empty
+// group once the feed is exhausted: every step retires exactly one group, which keeps the wait count a compile-time constant)
+__device__ __forceinline__ void ring_refill(RingFeed &f, uint32_t slot_lane, uint64_t policy) {
+    cp_async16(slot_lane, f.src, f.rem > 0 && f.lane_ok, policy);
+    cp_async_commit();
+    if (f.rem > 0) {
+        f.src += f.bytes;
+        if (--f.rem == 0 && f.rem2 != 0) {  // rare: switch to the following part
+            f.src = f.src2, f.rem = f.rem2, f.bytes = f.bytes2, f.rem2 = 0;
+            f.lane_ok = (threadIdx.x & 31) * 16u < f.bytes;
+        }
+    }
+}
+
+// consume this warp's run of one part from the ring (its super-tiles are the next run.n of the feed; the ring slots rotate
+// with `phase` = number of super-tiles consumed so far mod kRingDepth, carried from part to part)
+template <class Dec, int kSlotBytes>
+__device__ __forceinline__ void gemv3_run(const PackSegment seg, float *__restrict__ out, int M, int bs, uint32_t xs_addr,
+                                          uint32_t tab_lane, const WarpRun2 run, uint32_t ring /* this warp's slots */,
+                                          int &phase, RingFeed &f, uint64_t policy) {
+    constexpr int E = Dec::kE, D = kRingDepth;
+    using G = TcqGeom<E>;
+    const int lane = threadIdx.x & 31;
+    int word0, bitoff;
+    tcq_lane_addr<E>(lane, word0, bitoff);
+    const uint32_t rd = ring + (uint32_t)word0 * 4u;  // where this lane reads its payload inside slot 0
+    const uint32_t wr = ring + (uint32_t)lane * 16u;  // where this lane's copy lands inside slot 0
+    const uint32_t xstep = (uint32_t)bs * 64u;
+    uint32_t xa = gemv2_xbase(xs_addr, seg.ksuper0, bs) + (uint32_t)run.kh * xstep;
+    int row = seg.row0 + run.mh * 32;
+    int kleft = seg.ksuper - run.kh;  // steps until the strip ends (warp-uniform)
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    uint32_t so = (uint32_t)phase * kSlotBytes;  // byte offset of the slot to consume next
+    // keep the slot offset in an ordinary (per-lane) register: with a uniform-register offset ptxas 12.9 emitted the loop's
+    // LDGSTS as `[R+UR0], desc[UR1]` with UR0 / UR1 never written -- a wild shared-memory destination (illegal address)
+    asm volatile("mov.u32 %0, %0;" : "+r"(so));
+#pragma unroll 1
+    for (int s = 0; s < run.n; ++s) {
+        cp_async_wait<D - 1>();  // the oldest of the D groups in flight is this step's
+        __syncwarp();            // ... and every lane's 16 bytes of it have landed
+        uint32_t raw[G::kRawWords];
+#pragma unroll
+        for (int i = 0; i < G::kRawWords; ++i) raw[i] = lds_u32(rd + so + 4u * i);
+        uint32_t P[G::kWords];
+        tcq_align<E>(raw, bitoff, P);
+        gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+        // the payload has been consumed (the mma above depends on it): refill the slot with the super-tile D steps ahead
+        ring_refill(f, wr + so, policy);
+        so = (so == (D - 1) * kSlotBytes) ? 0u : so + kSlotBytes;
+        xa += xstep;
+        if (--kleft == 0) {  // rare: once per strip
+            gemv2_flush(out, M, bs, row, acc);
+            row += 32;
+            kleft = seg.ksuper;
+            xa = gemv2_xbase(xs_addr, seg.ksuper0, bs);
+        }
+    }
+    phase = (int)(so / kSlotBytes);
+    if (run.n > 0 && kleft != seg.ksuper) gemv2_flush(out, M, bs, row, acc);
 }
 
 inline int check_align(const void *p, size_t a, const char *name) {

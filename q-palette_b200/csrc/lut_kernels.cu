@@ -90,11 +90,9 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);  // compact lut copy
     uint32_t *xs = lc + lut_compact_words(E, r_single);
     const int lane = threadIdx.x & 31;
-    unsigned lo, hi;
-    split_range(split, blockIdx.x, lo, hi);
-    const WarpRun run = warp_run(seg, lo, hi, warp_in_cta());
-    uint32_t raw[kGemvDepth][TcqGeom<E>::kRawWords];
-    gemv_prefetch<E>(seg, run, raw);
+    const WarpRun2 run = warp_run2(seg, split, blockIdx.x * kGemvWarps + warp_in_cta());
+    uint32_t raw[kGemv2Depth][TcqGeom<E>::kRawWords];
+    gemv2_prefetch<E>(seg, run, raw);
     coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
     __syncthreads();
     lut_build_table<E, SPLIT>(tab, lc, r_single);
@@ -105,7 +103,7 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     __syncthreads();
     pdl_launch_dependents();
     const uint32_t tab_addr_lane = (lane & T::kLaneMask) << 2;  // the table starts the dynamic shared memory
-    gemv_run_segment<LutDecoder<E, SPLIT>>(seg, out, M, bs, reinterpret_cast<const uint8_t *>(xs), tab_addr_lane, run, raw);
+    gemv2_run<LutDecoder<E, SPLIT>>(seg, out, M, bs, smem_u32(xs), tab_addr_lane, run, raw, [] {});
 }
 
 template <int E, bool SPLIT>
@@ -139,7 +137,7 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
                         (prod.mode ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg,
-                       make_split((long)seg.strips * seg.ksuper, sm_count()), out, (const uint32_t *)x, lut,
+                       make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), out, (const uint32_t *)x, lut,
                        r_single, M, K, bs, prod));
     return check_launch("lut_gemv");
 }

@@ -138,7 +138,7 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
     simt_build_table<BITS, VEC>(tab, lc);
     // the dequantise form waits too: its output may alias a stream-ordered temporary the preceding kernel still reads
     pdl_wait();
-    if (GEMV) coop_copy_words(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
+    if (GEMV) coop_copy_words<true>(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
     __syncthreads();
     pdl_launch_dependents();
     const uint32_t tab_lane = (lane & T::kLaneMask) << 2;  // lane column; the table starts the dynamic shared memory (qp_dyn_smem)

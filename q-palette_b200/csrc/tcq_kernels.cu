@@ -35,6 +35,9 @@ __device__ __forceinline__ void phase_stamp(int i) {
 #define QP_PHASE(i)
 #endif
 
+#ifndef QP_GEMV_RING
+#define QP_GEMV_RING 0  // 1: codes staged through the per-warp bulk-copy ring (gemv3_run); 0: per-lane ld.global ring (gemv2_run)
+#endif
 constexpr int kTcqThreads = kGemvThreads;
 constexpr int kTcqWarps = kGemvWarps;
 
@@ -81,18 +84,22 @@ __device__ __forceinline__ void tcq_table_load(TcqTableRegs<S> &t, const uint32_
         // 128-byte row r holds 128 >> kStrideLog2 entries; this lane's 16-byte chunk belongs to entry ef (incl. the fold bit)
         const int ef = (r << (7 - T::kStrideLog2)) + ((lane & 7) >> (T::kStrideLog2 - 4));
         t.v[it] = (r < TcqTableRegs<S>::kRows) ? __ldg(tlut + (ef & ((1 << S) - 1))) : 0u;
-        if (T::kFold && (ef >> S)) t.v[it] ^= 0x8000u;                    // negate component 0 (low half)
     }
 }
 
+// the sign fold (negate component 0 for the upper half of the folded table) is applied here, at store time: nothing between
+// the load issue and this point may depend on the loaded values, so that their L2 round trip overlaps the rest of the prologue
 template <int S>
 __device__ __forceinline__ void tcq_table_store(uint32_t *tab, const TcqTableRegs<S> &t) {
+    using T = TcqTable<S>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll
     for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
         const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
-        if (r < TcqTableRegs<S>::kRows) t4[r * 8 + (lane & 7)] = make_uint4(t.v[it], t.v[it], t.v[it], t.v[it]);
+        const int ef = (r << (7 - T::kStrideLog2)) + ((lane & 7) >> (T::kStrideLog2 - 4));
+        const uint32_t v = (T::kFold && (ef >> S)) ? (t.v[it] ^ 0x8000u) : t.v[it];
+        if (r < TcqTableRegs<S>::kRows) t4[r * 8 + (lane & 7)] = make_uint4(v, v, v, v);
     }
 }
 
@@ -150,10 +157,13 @@ struct TcqDecoder {
 using TcqSegment = PackSegment;
 
 // ---- GEMV -----------------------------------------------------------------------------------------------------------
-template <int KVA, int KVB, int S>
+// FUSED = false: x is given (plain staging).  FUSED = true: the x-producer prologue of xprod.cuh (separate instantiation so
+// that the plain kernel's instruction footprint stays small).
+template <int KVA, int KVB, int S, bool FUSED>
 __global__ void __launch_bounds__(kTcqThreads, kGemvCtasPerSM)
 tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
-                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, XProd prod) {
+                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, int ring_off,
+                XProd prod) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float red[32];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
@@ -161,53 +171,76 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
 
     const int lane = threadIdx.x & 31;
     const int warp = warp_in_cta();
+    const int gwarp = blockIdx.x * kTcqWarps + warp;
     QP_PHASE(0);
-    // codebook loads first: their L2 round trip runs under the range arithmetic and the weight-prefetch issue below
+    // this warp's contiguous run of each part (a CTA's runs are adjacent: the CTA streams one contiguous byte range)
+    const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
+    // the HBM stream starts first (it has the longest latency and depends on nothing), then the codebook loads: both round
+    // trips run under the rest of the prologue
+#if QP_GEMV_RING
+    constexpr int kSlot = 64 * (KVA > KVB ? KVA : KVB);
+    WarpRun2 runB = {};
+    if constexpr (KVB != 0) runB = warp_run2(segB, splitB, gwarp);
+    RingFeed feed = make_feed(segA.codes, runA.lo, runA.n, 64 * KVA, KVB != 0 ? segB.codes : nullptr, runB.lo, runB.n,
+                              64 * (KVB != 0 ? KVB : KVA));
+    const uint64_t l2pol = l2_evict_first_policy();
+    const uint32_t ring = smem_u32(smem) + (uint32_t)ring_off + (uint32_t)warp * (kRingDepth * kSlot);
+#pragma unroll
+    for (int d = 0; d < kRingDepth; ++d) ring_refill(feed, ring + (uint32_t)d * kSlot + (uint32_t)lane * 16u, l2pol);
+#else
+    uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
+    gemv2_prefetch<KVA>(segA, runA, rawA);
+#endif
     TcqTableRegs<S> tregs;
     tcq_table_load<S>(tregs, tlut);
-    // this CTA's contiguous range of each part; its warps interleave inside it
-    unsigned loA, hiA;
-    split_range(splitA, blockIdx.x, loA, hiA);
-    const WarpRun runA = warp_run(segA, loA, hiA, warp);
-    uint32_t rawA[kGemvDepth][TcqGeom<KVA>::kRawWords];
-    gemv_prefetch<KVA>(segA, runA, rawA);  // weights do not depend on the previous kernel: fetch before the PDL wait
     QP_PHASE(1);
-    float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
-    // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
-    auto finish_prologue = [&](auto ch_tag) {
-        constexpr int CH = decltype(ch_tag)::value;
-        XPre<CH> pre;
-        if (prod.mode != 0) {
+    if constexpr (FUSED) {
+        float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
+        // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
+        auto finish_prologue = [&](auto ch_tag) {
+            constexpr int CH = decltype(ch_tag)::value;
+            XPre<CH> pre;
             xp_preload<CH>(pre, prod, K);
             xp_zero(prod);
-        }
+            tcq_table_store<S>(tab, tregs);
+            QP_PHASE(2);
+            pdl_wait();  // x (and out) are produced by the preceding kernel
+            QP_PHASE(3);
+            produce_x<CH>(xs, xscratch, red, prod, K, pre);
+        };
+        if (((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
+        else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
+    } else {
         tcq_table_store<S>(tab, tregs);
         QP_PHASE(2);
         pdl_wait();  // x (and out) are produced by the preceding kernel
         QP_PHASE(3);
-        if (prod.mode == 0) stage_x(xs, x32, K, bs);
-        else produce_x<CH>(xs, xscratch, red, prod, K, pre);
-    };
-    if (prod.mode == 0 || ((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
-    else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
+        stage_x(xs, x32, K, bs);
+    }
     __syncthreads();
     QP_PHASE(4);
     pdl_launch_dependents();
 
     const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
-    const uint8_t *xs_addr = reinterpret_cast<const uint8_t *>(xs);
+    const uint32_t xs_addr = smem_u32(xs);
+#if QP_GEMV_RING
+    // the ring carries part A's run followed by part B's: the stream never drains between the parts
+    int phase = 0;
+    gemv3_run<TcqDecoder<KVA, S>, kSlot>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, ring, phase, feed, l2pol);
+    if constexpr (KVB != 0)
+        gemv3_run<TcqDecoder<KVB, S>, kSlot>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, ring, phase, feed, l2pol);
+#else
     if constexpr (KVB == 0) {
-        gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA);
+        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {});
     } else {
-        unsigned loB, hiB;
-        split_range(splitB, blockIdx.x, loB, hiB);
-        const WarpRun runB = warp_run(segB, loB, hiB, warp);
-        uint32_t rawB[kGemvDepth][TcqGeom<KVB>::kRawWords];
-        // the second part's first loads are issued while the first part drains
-        gemv_run_segment<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
-                                             [&] { gemv_prefetch<KVB>(segB, runB, rawB); });
-        gemv_run_segment<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB);
+        const WarpRun2 runB = warp_run2(segB, splitB, gwarp);
+        uint32_t rawB[kGemv2Depth][TcqGeom<KVB>::kRawWords];
+        // the second part's first loads are issued while the first part's tail drains
+        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
+                                      [&] { gemv2_prefetch<KVB>(segB, runB, rawB); });
+        gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {});
     }
+#endif
 #ifdef QP_PROFILE_PHASES
     QP_PHASE(5);  // thread 0's warp done
     __syncthreads();
@@ -267,20 +300,34 @@ static int make_segments(TcqLaunch &L, const void *codes1, const void *codes2, i
     return QP_OK;
 }
 
+// shared memory of the code ring (+ its mbarriers) behind the codebook and the x stage
+inline size_t tcq_ring_bytes(int kv_max) {
+#if QP_GEMV_RING
+    return (size_t)kTcqWarps * kRingDepth * 64 * (size_t)kv_max;
+#else
+    (void)kv_max;
+    return 0;
+#endif
+}
+
 template <int KVA, int KVB, int S>
 static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void *tlut, int M, int K, int bs,
                        const XProd &prod, cudaStream_t st) {
-    auto kern = tcq_gemv_kernel<KVA, KVB, S>;
-    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (prod.mode ? (size_t)K * 4 : 0);
-    QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
-    static DeviceOnce configured;
-    if (configured.first()) {
+    const bool fused = prod.mode != 0;
+    auto kern = fused ? tcq_gemv_kernel<KVA, KVB, S, true> : tcq_gemv_kernel<KVA, KVB, S, false>;
+    const size_t ring_off = ((size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0) + 15) & ~(size_t)15;
+    const size_t smem = ring_off + tcq_ring_bytes(KVA > KVB ? KVA : KVB);
+    QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the shared-memory budget of the %s GEMV", K,
+                 fused ? "fused-prologue" : "plain");
+    static DeviceOnce configured[2];
+    if (configured[fused].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
     }
     const int nctas = sm_count() * kGemvCtasPerSM;
+    const int nwarps = nctas * kTcqWarps;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
-                       make_split((long)L.a.strips * L.a.ksuper, nctas), make_split((long)L.b.strips * L.b.ksuper, nctas),
-                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
+                       make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, (int)ring_off, prod));
     return check_launch("tcq_gemv");
 }
 
@@ -319,6 +366,10 @@ static int launch_dequant(const TcqLaunch &L, __half *W, const void *tlut, int K
 
 static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, const void *tlut, int M, int K, int bs,
                          const XProd &prod, cudaStream_t st) {
+#ifdef QP_FAST_BUILD  // experiments: only the headline instantiation (tcomb_6_7, S = 9), seconds instead of minutes to compile
+    if (L.kva == 6 && L.kvb == 7 && S == 9) return launch_gemv<6, 7, 9>(L, out, x, tlut, M, K, bs, prod, st);
+    return fail(QP_ERR_ARG, "QP_FAST_BUILD library: only tcomb_6_7 / S = 9");
+#else
     if (L.kvb == 0) {
         switch (L.kva) {
             case 2: QP_TCQ_SINGLE(launch_gemv, 2, L, out, x, tlut, M, K, bs, prod, st)
@@ -355,6 +406,7 @@ static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, c
         return dispatch_gemv(b, S, out, x, tlut, M, K, bs, prod, st);
     }
     return fail(QP_ERR_ARG, "unsupported TCQ configuration S=%d KV=(%d,%d)", S, L.kva, L.kvb);
+#endif
 }
 
 static int dispatch_dequant(const TcqLaunch &L, int S, __half *W, const void *tlut, int K, cudaStream_t st) {
@@ -402,7 +454,7 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
     if ((rc = check_align(tlut_f16, 4, "tlut")) != QP_OK) return rc;
     // x lives in shared memory next to the 128 KiB codebook: process the batch in chunks that fit
-    const size_t avail = (size_t)kMaxSmem - 256 - 128 * 1024;
+    const size_t avail = (size_t)kMaxSmem - 256 - 128 * 1024 - 16 - tcq_ring_bytes(KV1 > KV2 ? KV1 : KV2);
     int chunk = (int)(avail / ((size_t)K * 2));
     QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
     if (chunk > bs) chunk = bs;

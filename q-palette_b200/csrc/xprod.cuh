@@ -130,8 +130,11 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
         const bool ok = c < nch;
-        hv[j] = ok ? __ldg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
-        av[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // activations / accumulators are rewritten by other kernels within one decode step and kernels overlap under programmatic
+        // dependent launch: read them at L2 (ld.global.cg), never through the non-coherent L1 path (measured round 2: with
+        // ld.global.nc a CTA could see a stale line of `acc` / `src` and the fused launch list diverged from the un-fused one)
+        hv[j] = ok ? __ldcg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
+        av[j] = (ok && p.acc) ? __ldcg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     QP_XPHASE(1);  // loads issued, zero slices stored
     const __half hs = __float2half(p.acc_scale);

