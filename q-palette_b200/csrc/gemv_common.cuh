@@ -95,29 +95,6 @@ __device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict
     }
 }
 
-// add one 32-row strip of partial sums to out (bs, M): acc[ml] is the C fragment of rows row0 + 16*ml + {lane/4, +8},
-// batch columns 2*(lane%4), +1.  Zeroes the accumulators.
-__device__ __forceinline__ void gemv_flush(float *__restrict__ out, int M, int bs, int row0, int lane,
-                                           float (&acc)[2][4]) {
-    const int r = row0 + (lane >> 2);
-    const int c0 = 2 * (lane & 3), c1 = c0 + 1;
-#pragma unroll
-    for (int ml = 0; ml < 2; ++ml) {
-        const int r0 = r + ml * 16;
-        if (c0 < bs) {
-            atomicAdd(out + (size_t)c0 * M + r0, acc[ml][0]);
-            atomicAdd(out + (size_t)c0 * M + r0 + 8, acc[ml][2]);
-        }
-        if (c1 < bs) {
-            atomicAdd(out + (size_t)c1 * M + r0, acc[ml][1]);
-            atomicAdd(out + (size_t)c1 * M + r0 + 8, acc[ml][3]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[ml][j] = 0.f;
-    }
-}
-
-
 // warp index / grid-wide warp id as provably warp-uniform values (lets ptxas keep run bounds in uniform registers and
 // drop the convergence barriers around the shuffles)
 __device__ __forceinline__ int warp_in_cta() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
@@ -133,16 +110,12 @@ struct PackSegment {
 #ifndef QP_GEMV_THREADS
 #define QP_GEMV_THREADS 768
 #endif
-#ifndef QP_GEMV_DEPTH
-#define QP_GEMV_DEPTH 3
-#endif
 #ifndef QP_GEMV_CTAS
 #define QP_GEMV_CTAS 1
 #endif
 constexpr int kGemvCtasPerSM = QP_GEMV_CTAS;    // experiments: 2 CTAs of 384 threads per SM (needs a <= 64 KiB codebook)
 constexpr int kGemvThreads = QP_GEMV_THREADS;   // one CTA per SM (the lane-replicated codebook takes 128 KiB)
 constexpr int kGemvWarps = kGemvThreads / 32;
-constexpr int kGemvDepth = QP_GEMV_DEPTH;       // super-tiles prefetched ahead per warp (register staged)
 
 // even split of T work items over the grid's warps, computed on the host: warp w owns
 // [w*base + min(w, rem), ... + base + (w < rem))
@@ -204,141 +177,6 @@ __device__ __forceinline__ void pack_load_raw_pred(uint32_t (&raw)[TcqGeom<E>::k
     }
 }
 
-// Work assignment: the part's super-tiles [0, T) are split into one contiguous range per CTA; inside the CTA the warps
-// interleave (warp w takes range_lo + w, + kGemvWarps, ...).  The CTA therefore streams a single moving window of
-// kGemvWarps * 64*E contiguous bytes (DRAM-page friendly, like a copy kernel) while a warp's consecutive super-tiles still
-// belong to the same 32-row strip most of the time, so accumulators are flushed only when the strip changes.
-struct WarpRun {
-    int n;      // super-tiles this warp processes
-    int mh, kh; // strip / column of the first one
-    size_t first;  // its index
-};
-__device__ __forceinline__ WarpRun warp_run(const PackSegment seg, unsigned clo, unsigned chi, int warp) {
-    WarpRun r;
-    const int span = (int)(chi - clo);
-    r.n = span > warp ? (span - warp + kGemvWarps - 1) / kGemvWarps : 0;
-    r.first = (size_t)clo + warp;
-    const unsigned it0 = clo + (unsigned)warp;
-    r.mh = (int)(it0 / (unsigned)seg.ksuper);
-    r.kh = (int)(it0 - (unsigned)r.mh * (unsigned)seg.ksuper);
-    return r;
-}
-
-// issue the first kGemvDepth payload loads of this warp's run
-template <int E>
-__device__ __forceinline__ void gemv_prefetch(const PackSegment seg, const WarpRun run,
-                                              uint32_t (&raw)[kGemvDepth][TcqGeom<E>::kRawWords]) {
-    using G = TcqGeom<E>;
-    constexpr size_t kStride = (size_t)kGemvWarps * (G::kSuperBytes / 4);
-    const int lane = threadIdx.x & 31;
-    int word0, bitoff;
-    tcq_lane_addr<E>(lane, word0, bitoff);
-    const uint32_t *p = seg.codes + word0 + run.first * (G::kSuperBytes / 4);
-#pragma unroll
-    for (int d = 0; d < kGemvDepth; ++d) {
-#pragma unroll
-        for (int i = 0; i < G::kRawWords; ++i) raw[d][i] = 0u;
-        pack_load_raw_pred<E>(raw[d], p + d * kStride, d < run.n);
-    }
-}
-
-// one super-tile: consume slot `raw` (decode -> 4 mma), refill it with the super-tile kGemvDepth steps ahead
-template <class Dec, bool kRefillAlways>
-__device__ __forceinline__ void gemv_step(uint32_t (&raw)[TcqGeom<Dec::kE>::kRawWords], const uint32_t *pnext,
-                                          bool refill, int bitoff, int lane, uint32_t tab_lane,
-                                          const uint8_t *xs_lane, bool xvalid, float (&acc)[2][4]) {
-    constexpr int E = Dec::kE;
-    using G = TcqGeom<E>;
-    uint32_t P[G::kWords];
-    tcq_align<E>(raw, bitoff, P);  // the slot's registers are dead after this: the refill below can land in them
-    pack_load_raw_pred<E>(raw, pnext, kRefillAlways ? true : refill);
-    uint4 xb = make_uint4(0u, 0u, 0u, 0u);
-    if (xvalid) xb = *reinterpret_cast<const uint4 *>(xs_lane);
-    uint32_t frag[4][4];  // [tile = kl*2+ml][register]
-    Dec::decode(P, lane, tab_lane, frag);
-    mma_16816(acc[0], frag[0][0], frag[0][1], frag[0][2], frag[0][3], xb.x, xb.y);
-    mma_16816(acc[1], frag[1][0], frag[1][1], frag[1][2], frag[1][3], xb.x, xb.y);
-    mma_16816(acc[0], frag[2][0], frag[2][1], frag[2][2], frag[2][3], xb.z, xb.w);
-    mma_16816(acc[1], frag[3][0], frag[3][1], frag[3][2], frag[3][3], xb.z, xb.w);
-}
-
-// stream this warp's run of one part: decode (Dec) -> A fragments -> mma with x (B fragments from shared memory) ->
-// fp32 atomics per finished 32-row strip.
-//   Dec::kE                              bits per weight pair (payload geometry TcqGeom<kE>)
-//   Dec::decode(P, lane, tab_lane, frag) 16 half2 registers of the (lane, super-tile) from its aligned payload words
-// `between` runs once after the steady state and before the drain (used to issue the next part's first loads so its DRAM
-// latency hides behind this part's tail).
-template <class Dec, class Between>
-__device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *__restrict__ out, int M, int bs,
-                                                 const uint8_t *xs, uint32_t tab_lane, const WarpRun run,
-                                                 uint32_t (&raw)[kGemvDepth][TcqGeom<Dec::kE>::kRawWords],
-                                                 Between between) {
-    constexpr int E = Dec::kE;
-    using G = TcqGeom<E>;
-    constexpr size_t kStride = (size_t)kGemvWarps * (G::kSuperBytes / 4);  // words between a warp's consecutive super-tiles
-    const int lane = threadIdx.x & 31;
-    int word0, bitoff;
-    tcq_lane_addr<E>(lane, word0, bitoff);
-    const int nq = lane >> 2, q = lane & 3;
-    const bool xvalid = nq < bs;
-
-    float acc[2][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    int n = run.n;
-    int mh = run.mh, kh = run.kh;
-    const uint32_t *p = seg.codes + word0 + run.first * (G::kSuperBytes / 4) + kGemvDepth * kStride;
-    const uint8_t *xs_q = xs + ((size_t)seg.ksuper0 * bs + nq) * 64 + q * 16;
-    const int xstep = bs * 64;
-
-    auto advance = [&]() {
-        kh += kGemvWarps;
-        if (kh >= seg.ksuper) {  // this warp's next super-tile is in a later strip: flush (rarely more than one wrap)
-            gemv_flush(out, M, bs, seg.row0 + mh * 32, lane, acc);
-            do {
-                kh -= seg.ksuper;
-                ++mh;
-            } while (kh >= seg.ksuper);
-        }
-    };
-
-    // steady state: every refill is in range
-    while (n >= 2 * kGemvDepth) {
-#pragma unroll
-        for (int d = 0; d < kGemvDepth; ++d) {
-            gemv_step<Dec, true>(raw[d], p + d * kStride, true, bitoff, lane, tab_lane, xs_q + kh * xstep, xvalid, acc);
-            advance();
-        }
-        p += kGemvDepth * kStride;
-        n -= kGemvDepth;
-    }
-    between();
-    // drain: fewer than 2*kGemvDepth left; refills are predicated
-    while (n > 0) {
-#pragma unroll
-        for (int d = 0; d < kGemvDepth; ++d) {
-            if (d < n) {
-                gemv_step<Dec, false>(raw[d], p + d * kStride, d + kGemvDepth < n, bitoff, lane, tab_lane,
-                                      xs_q + kh * xstep, xvalid, acc);
-                if (d + 1 < n || n > kGemvDepth) advance();
-            }
-        }
-        p += kGemvDepth * kStride;
-        n -= kGemvDepth;
-    }
-    if (run.n > 0) gemv_flush(out, M, bs, seg.row0 + mh * 32, lane, acc);
-}
-
-template <class Dec>
-__device__ __forceinline__ void gemv_run_segment(const PackSegment seg, float *__restrict__ out, int M, int bs,
-                                                 const uint8_t *xs, uint32_t tab_lane, const WarpRun run,
-                                                 uint32_t (&raw)[kGemvDepth][TcqGeom<Dec::kE>::kRawWords]) {
-    gemv_run_segment<Dec>(seg, out, M, bs, xs, tab_lane, run, raw, [] {});
-}
-
 // decode the warp's share of one part and write fp16 W (M, K) row-major
 template <class Dec>
 __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __half *__restrict__ W, int K,
@@ -375,7 +213,7 @@ __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __hal
 }
 
 // =====================================================================================================================
-// v2 streaming skeleton (round 2).  Same data path as above -- per-lane streaming loads into a register ring, decode,
+// Streaming skeleton (round 2).  Per-lane streaming loads into a register ring, decode,
 // mma.m16n8k16 against x fragments in shared memory, fp32 atomics per finished strip -- but organised for the fewest issued
 // instructions per super-tile and a small instruction footprint (the round-1 loop spent ~35 of its 155 warp-instructions
 // per super-tile on strip / x-address bookkeeping and was 100 KB of SASS per instantiation):
@@ -530,131 +368,6 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
         }
     }
     if (n > 0 && kleft != seg.ksuper) gemv2_flush(out, M, bs, row, acc);
-}
-
-// =====================================================================================================================
-// v3: the packed codes reach the decode through a per-warp SHARED-MEMORY RING filled by 16-byte asynchronous copies
-// (cp.async.cg, LDGSTS) instead of per-lane ld.global into registers.  Why (measured, tools/ubench_mio.cu on B200): a warp's
-// per-lane 32-bit loads at a 12 / 14-byte lane stride cost 4.8 SM-cycles of L1 request bandwidth EACH -- every one of the 3-4
-// loads of a super-tile touches all of its 12-14 sectors, 3-4x the useful sector requests -- i.e. 15-21 of the ~27 cycles a
-// super-tile may cost per SM, while one fully coalesced 16-byte-per-lane copy of the same 384-448 bytes costs ~6 and a
-// lane-replicated LDS.32 gather 0.27.  The ring is private to a warp (no cross-warp synchronisation): kRingDepth slots of one
-// super-tile, one cp.async group per slot; a step waits for the oldest group, reads its payload with 3-4 LDS.32 (any lane
-// alignment: the slot is a flat copy of the super-tile), decodes, and refills the slot with the super-tile kRingDepth ahead.
-// (A 1-D bulk copy -- cp.async.bulk + mbarrier, zero LSU cost -- was built first: its uniform-register operands cost ptxas an
-// elect-one loop and 5-7 R2UR per copy, ~25 issue slots per super-tile against ~10 here; the loop is issue-bound next.)
-// =====================================================================================================================
-#ifndef QP_RING_DEPTH
-#define QP_RING_DEPTH 4
-#endif
-constexpr int kRingDepth = QP_RING_DEPTH;
-
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred, uint64_t policy) {
-    (void)policy;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
-        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst),
-        "l"(src), "r"((int)pred)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// the stream of super-tiles a warp will consume: its run of part A followed by its run of part B (rem2 = 0: single part).
-// src already includes this lane's 16-byte column (lane * 16); `lane_ok` = this lane's column lies inside the super-tile.
-struct RingFeed {
-    const uint8_t *src;   // next super-tile to fetch (+ lane * 16)
-    int rem;              // super-tiles of the current part still to fetch
-    uint32_t bytes;       // bytes per super-tile of the current part
-    bool lane_ok;
-    const uint8_t *src2;  // the following part
-    int rem2;
-    uint32_t bytes2;
-};
-__device__ __forceinline__ RingFeed make_feed(const void *a, size_t lo_a, int n_a, int bytes_a, const void *b, size_t lo_b, int n_b,
-                                              int bytes_b) {
-    const uint32_t l16 = (threadIdx.x & 31) * 16u;
-    RingFeed f;
-    f.src = reinterpret_cast<const uint8_t *>(a) + lo_a * (size_t)bytes_a + l16;
-    f.rem = n_a, f.bytes = (uint32_t)bytes_a, f.lane_ok = l16 < (uint32_t)bytes_a;
-    f.src2 = b ? reinterpret_cast<const uint8_t *>(b) + lo_b * (size_t)bytes_b + l16 : nullptr;
-    f.rem2 = b ? n_b : 0, f.bytes2 = (uint32_t)bytes_b;
-    if (f.rem == 0 && f.rem2 != 0) {
-        f.src = f.src2, f.rem = f.rem2, f.bytes = f.bytes2, f.rem2 = 0;
-        f.lane_ok = l16 < f.bytes;
-    }
-    return f;
-}
-// start the copy of the next super-tile of the feed into `slot_lane` (= slot address + lane * 16) and close its group (an empty
-// group once the feed is exhausted: every step retires exactly one group, which keeps the wait count a compile-time constant)
-__device__ __forceinline__ void ring_refill(RingFeed &f, uint32_t slot_lane, uint64_t policy) {
-    cp_async16(slot_lane, f.src, f.rem > 0 && f.lane_ok, policy);
-    cp_async_commit();
-    if (f.rem > 0) {
-        f.src += f.bytes;
-        if (--f.rem == 0 && f.rem2 != 0) {  // rare: switch to the following part
-            f.src = f.src2, f.rem = f.rem2, f.bytes = f.bytes2, f.rem2 = 0;
-            f.lane_ok = (threadIdx.x & 31) * 16u < f.bytes;
-        }
-    }
-}
-
-// consume this warp's run of one part from the ring (its super-tiles are the next run.n of the feed; the ring slots rotate
-// with `phase` = number of super-tiles consumed so far mod kRingDepth, carried from part to part)
-template <class Dec, int kSlotBytes>
-__device__ __forceinline__ void gemv3_run(const PackSegment seg, float *__restrict__ out, int M, int bs, uint32_t xs_addr,
-                                          uint32_t tab_lane, const WarpRun2 run, uint32_t ring /* this warp's slots */,
-                                          int &phase, RingFeed &f, uint64_t policy) {
-    constexpr int E = Dec::kE, D = kRingDepth;
-    using G = TcqGeom<E>;
-    const int lane = threadIdx.x & 31;
-    int word0, bitoff;
-    tcq_lane_addr<E>(lane, word0, bitoff);
-    const uint32_t rd = ring + (uint32_t)word0 * 4u;  // where this lane reads its payload inside slot 0
-    const uint32_t wr = ring + (uint32_t)lane * 16u;  // where this lane's copy lands inside slot 0
-    const uint32_t xstep = (uint32_t)bs * 64u;
-    uint32_t xa = gemv2_xbase(xs_addr, seg.ksuper0, bs) + (uint32_t)run.kh * xstep;
-    int row = seg.row0 + run.mh * 32;
-    int kleft = seg.ksuper - run.kh;  // steps until the strip ends (warp-uniform)
-    float acc[2][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    uint32_t so = (uint32_t)phase * kSlotBytes;  // byte offset of the slot to consume next
-    // keep the slot offset in an ordinary (per-lane) register: with a uniform-register offset ptxas 12.9 emitted the loop's
-    // LDGSTS as `[R+UR0], desc[UR1]` with UR0 / UR1 never written -- a wild shared-memory destination (illegal address)
-    asm volatile("mov.u32 %0, %0;" : "+r"(so));
-#pragma unroll 1
-    for (int s = 0; s < run.n; ++s) {
-        cp_async_wait<D - 1>();  // the oldest of the D groups in flight is this step's
-        __syncwarp();            // ... and every lane's 16 bytes of it have landed
-        uint32_t raw[G::kRawWords];
-#pragma unroll
-        for (int i = 0; i < G::kRawWords; ++i) raw[i] = lds_u32(rd + so + 4u * i);
-        uint32_t P[G::kWords];
-        tcq_align<E>(raw, bitoff, P);
-        gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
-        // the payload has been consumed (the mma above depends on it): refill the slot with the super-tile D steps ahead
-        ring_refill(f, wr + so, policy);
-        so = (so == (D - 1) * kSlotBytes) ? 0u : so + kSlotBytes;
-        xa += xstep;
-        if (--kleft == 0) {  // rare: once per strip
-            gemv2_flush(out, M, bs, row, acc);
-            row += 32;
-            kleft = seg.ksuper;
-            xa = gemv2_xbase(xs_addr, seg.ksuper0, bs);
-        }
-    }
-    phase = (int)(so / kSlotBytes);
-    if (run.n > 0 && kleft != seg.ksuper) gemv2_flush(out, M, bs, row, acc);
 }
 
 inline int check_align(const void *p, size_t a, const char *name) {

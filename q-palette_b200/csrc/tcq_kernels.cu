@@ -35,9 +35,6 @@ __device__ __forceinline__ void phase_stamp(int i) {
 #define QP_PHASE(i)
 #endif
 
-#ifndef QP_GEMV_RING
-#define QP_GEMV_RING 0  // 1: codes staged through the per-warp bulk-copy ring (gemv3_run); 0: per-lane ld.global ring (gemv2_run)
-#endif
 constexpr int kTcqThreads = kGemvThreads;
 constexpr int kTcqWarps = kGemvWarps;
 
@@ -162,8 +159,7 @@ using TcqSegment = PackSegment;
 template <int KVA, int KVB, int S, bool FUSED>
 __global__ void __launch_bounds__(kTcqThreads, kGemvCtasPerSM)
 tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
-                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, int ring_off,
-                XProd prod) {
+                const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, XProd prod) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float red[32];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
@@ -177,20 +173,8 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
     // the HBM stream starts first (it has the longest latency and depends on nothing), then the codebook loads: both round
     // trips run under the rest of the prologue
-#if QP_GEMV_RING
-    constexpr int kSlot = 64 * (KVA > KVB ? KVA : KVB);
-    WarpRun2 runB = {};
-    if constexpr (KVB != 0) runB = warp_run2(segB, splitB, gwarp);
-    RingFeed feed = make_feed(segA.codes, runA.lo, runA.n, 64 * KVA, KVB != 0 ? segB.codes : nullptr, runB.lo, runB.n,
-                              64 * (KVB != 0 ? KVB : KVA));
-    const uint64_t l2pol = l2_evict_first_policy();
-    const uint32_t ring = smem_u32(smem) + (uint32_t)ring_off + (uint32_t)warp * (kRingDepth * kSlot);
-#pragma unroll
-    for (int d = 0; d < kRingDepth; ++d) ring_refill(feed, ring + (uint32_t)d * kSlot + (uint32_t)lane * 16u, l2pol);
-#else
     uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
     gemv2_prefetch<KVA>(segA, runA, rawA);
-#endif
     TcqTableRegs<S> tregs;
     tcq_table_load<S>(tregs, tlut);
     QP_PHASE(1);
@@ -223,13 +207,6 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
 
     const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
     const uint32_t xs_addr = smem_u32(xs);
-#if QP_GEMV_RING
-    // the ring carries part A's run followed by part B's: the stream never drains between the parts
-    int phase = 0;
-    gemv3_run<TcqDecoder<KVA, S>, kSlot>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, ring, phase, feed, l2pol);
-    if constexpr (KVB != 0)
-        gemv3_run<TcqDecoder<KVB, S>, kSlot>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, ring, phase, feed, l2pol);
-#else
     if constexpr (KVB == 0) {
         gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {});
     } else {
@@ -240,7 +217,6 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
                                       [&] { gemv2_prefetch<KVB>(segB, runB, rawB); });
         gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {});
     }
-#endif
 #ifdef QP_PROFILE_PHASES
     QP_PHASE(5);  // thread 0's warp done
     __syncthreads();
@@ -300,23 +276,12 @@ static int make_segments(TcqLaunch &L, const void *codes1, const void *codes2, i
     return QP_OK;
 }
 
-// shared memory of the code ring (+ its mbarriers) behind the codebook and the x stage
-inline size_t tcq_ring_bytes(int kv_max) {
-#if QP_GEMV_RING
-    return (size_t)kTcqWarps * kRingDepth * 64 * (size_t)kv_max;
-#else
-    (void)kv_max;
-    return 0;
-#endif
-}
-
 template <int KVA, int KVB, int S>
 static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void *tlut, int M, int K, int bs,
                        const XProd &prod, cudaStream_t st) {
     const bool fused = prod.mode != 0;
     auto kern = fused ? tcq_gemv_kernel<KVA, KVB, S, true> : tcq_gemv_kernel<KVA, KVB, S, false>;
-    const size_t ring_off = ((size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0) + 15) & ~(size_t)15;
-    const size_t smem = ring_off + tcq_ring_bytes(KVA > KVB ? KVA : KVB);
+    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the shared-memory budget of the %s GEMV", K,
                  fused ? "fused-prologue" : "plain");
     static DeviceOnce configured[2];
@@ -327,7 +292,7 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     const int nwarps = nctas * kTcqWarps;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
                        make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
-                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, (int)ring_off, prod));
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
     return check_launch("tcq_gemv");
 }
 
@@ -454,7 +419,7 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     if ((rc = check_align(x_f16, 16, "x")) != QP_OK) return rc;
     if ((rc = check_align(tlut_f16, 4, "tlut")) != QP_OK) return rc;
     // x lives in shared memory next to the 128 KiB codebook: process the batch in chunks that fit
-    const size_t avail = (size_t)kMaxSmem - 256 - 128 * 1024 - 16 - tcq_ring_bytes(KV1 > KV2 ? KV1 : KV2);
+    const size_t avail = (size_t)kMaxSmem - 256 - 128 * 1024;
     int chunk = (int)(avail / ((size_t)K * 2));
     QP_CHECK_ARG(chunk >= 1, "K = %d too large for the shared-memory x stage", K);
     if (chunk > bs) chunk = bs;
