@@ -140,6 +140,9 @@ typedef struct qp_xchg {
 int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
                            float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
                            int do_had, float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
+/* The exchange of qp_fused_norm_had_xchg alone (clear zero_ptr, push own slice, wait for the peers'): for a consumer that is a
+ * GEMV with the fused x-producer prologue (qp_*_gemv_fused), which then reads the completed buffer from the local region. */
+int qp_xchg_gather(float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
 /* Row-sharded SiLU*mul + Hadamard: acc_local / wscale_local = [up | gate] of this rank's I / nranks rows; one CTA per local
  * 512-element block pushes its transformed block into the exchange buffer at xc->offset (I floats) of every rank, then every
  * rank finishes the transform from its own copy: x_out = the complete fp16 vector on every rank.  *sync_counter: a local

@@ -249,6 +249,18 @@ fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, co
     }
 }
 
+// The exchange alone: complete a row-sharded buffer in place on every rank (push own slice to the peers, wait for theirs) and
+// clear `zero_ptr` first.  Used in front of a GEMV whose fused prologue (xprod.cuh) consumes the completed buffer: the
+// residual / RMSNorm / Hadamard work then runs in all of the GEMV's CTAs instead of one 1024-thread CTA.
+__global__ void __launch_bounds__(kDecThreads, 1)
+xchg_gather_kernel(float *__restrict__ zero_ptr, int zero_count, XchgDev xc) {
+    pdl_wait();
+    pdl_launch_dependents();
+    // clear first: a peer only pushes into the cleared buffer after it has seen this rank's flag of this site
+    if (zero_ptr) zero_words4(zero_ptr, zero_count);
+    peer_allgather(xc);
+}
+
 // acc = [up (I) | gate (I)] fp32 -> y = silu(gate)*up (fp16 rounding points as the reference graph) -> *su -> had -> x
 template <int CH>
 __global__ void __launch_bounds__(kDecThreads, 1)
@@ -984,6 +996,29 @@ extern "C" int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeb
     d.site = xc->site;
     return fused_norm_had_impl(x_out_f16, h_f16, h_writeback, acc, wscale_f16, acc_scale, norm_w_f16, eps, su_f16, n, had_scale,
                                do_had, zero_ptr, zero_count, d, stream);
+}
+
+static int make_xchg_dev(XchgDev &d, const qp_xchg *xc) {
+    QP_CHECK_ARG(xc && xc->peer_base && xc->peer_flags && xc->epoch, "NULL exchange descriptor");
+    QP_CHECK_ARG(xc->nranks >= 1 && xc->nranks <= 32 && xc->rank >= 0 && xc->rank < xc->nranks, "bad rank %d of %d", xc->rank, xc->nranks);
+    QP_CHECK_ARG(xc->slice_bytes > 0 && xc->slice_bytes % 16 == 0 && xc->offset % 16 == 0, "exchange slices must be 16-byte multiples");
+    d.peer_base = (unsigned char *const *)xc->peer_base;
+    d.peer_flags = (unsigned *const *)xc->peer_flags;
+    d.epoch = xc->epoch + xc->site;
+    d.offset = xc->offset;
+    d.slice_bytes = xc->slice_bytes;
+    d.rank = xc->rank;
+    d.nranks = xc->nranks;
+    d.site = xc->site;
+    return QP_OK;
+}
+
+extern "C" int qp_xchg_gather(float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream) {
+    XchgDev d;
+    int rc = make_xchg_dev(d, xc);
+    if (rc != QP_OK) return rc;
+    QP_CUDA(launch_pdl(xchg_gather_kernel, dim3(1), dim3(kDecThreads), 0, (cudaStream_t)stream, zero_ptr, zero_count, d));
+    return check_launch("xchg_gather");
 }
 
 // ---- exchange region management (CUDA IPC) -------------------------------------------------------------------------------

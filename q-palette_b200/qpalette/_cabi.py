@@ -34,6 +34,7 @@ SIGNATURES = {
     "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
     "qp_fused_norm_had_xchg": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp, _vp],
+    "qp_xchg_gather": [_vp, _i, _vp, _vp],
     "qp_silu_mul_had_grid_xchg": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp, _vp],
     "qp_set_spin_timeout_ms": [ctypes.c_longlong],
     "qp_peer_alloc": [_vp, ctypes.c_size_t],

@@ -152,7 +152,7 @@ class DecodeRunner:
         self.p2p = p2p and world > 1
         self.L = num_layers or shape.num_hidden_layers
         self.max_seq = max_seq
-        self.fused = fused and world == 1   # GEMV-prologue fusion of the glue (single-GPU path)
+        self.fused = fused   # GEMV-prologue fusion of the glue (row-sharded: only with the peer exchange, decided below)
         qdict = qdict or uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9")
         merge_info = merge_info or [["merge_qkv", "merge_ug"]] * shape.num_hidden_layers
         g = torch.Generator(device=self.dev)
@@ -277,6 +277,8 @@ class DecodeRunner:
         # row-sharded form: the I / 512 blocks must split evenly over the ranks (and the shape be instantiated)
         self.silu_grid_tp = (self.p2p and self.I % (512 * world) == 0 and
                              any(self.I == kf * r * 512 for kf, r in ((28, 1), (28, 2), (1, 8), (1, 16))))
+        if world > 1 and not (self.p2p and self.silu_grid_tp):
+            self.fused = False  # the NCCL baseline and shapes without the multi-CTA exchange kernel keep the un-fused list
         self.graph = None
         self.steps_done = 0          # host-side count of positions written since reset(): the KV cache holds max_seq rows
         self.lm_head_bytes = self.lm_head.numel() * 2
@@ -290,8 +292,75 @@ class DecodeRunner:
     # -----------------------------------------------------------------------------------------------------------------
     def _step(self):
         if self.fused:
-            return self._step_fused()
+            return self._step_fused() if self.world == 1 else self._step_fused_tp()
         return self._step_unfused()
+
+    def _step_fused_tp(self):
+        """row-sharded decode step with the glue fused into the GEMV prologues: per layer 3 exchange kernels (complete the
+        gathered buffer in place over NVLink peer memory, qp_xchg_gather) + 4 GEMVs (3 of them computing residual / RMSNorm /
+        sign / Hadamard of the completed buffer in all of their CTAs) + attention + the exchanging SiLU*mul/Hadamard kernel.
+        Replaces the three single-CTA 8192-point norm/Hadamard kernels of the un-fused sharded list (~7 us each).
+        Exchange sites and accumulator-clearing duties are those of _step_unfused (clear-before-flag protocol)."""
+        L, st = lib(), torch.cuda.current_stream().cuda_stream
+        sh, H, I, world, rank = self.shape, self.H, self.I, self.world, self.rank
+        n0 = _cabi.launch_count()
+        p = lambda t: t.data_ptr() if t is not None else None
+        s_h, s_i, S = 1.0 / (math.sqrt(H) * 64.0), 1.0 / (math.sqrt(I) * 64.0), 64.0
+        Ho = H // world
+        keep = self._xchg_keep = []
+        hc, ho = self.h, self.h2
+        check(L.qp_embed(p(hc), p(self.embed), p(self.token), H, st))
+
+        def gather(name, site, zero):
+            xc = self.region.xchg(name, site)
+            keep.append(xc)
+            check(L.qp_xchg_gather(p(zero), zero.numel() if zero is not None else 0, ctypes.byref(xc), st))
+
+        def xp(src, h_out=None, acc=None, ws=None, norm=None, su=None, scale=s_h):
+            return _cabi.XProd(p(src), p(h_out), p(acc), p(ws), S, p(norm), sh.rms_norm_eps, p(su), scale, None, None, 0, None, 0)
+
+        def run_group(projs, acc_buf, acc_off, prod):
+            lead = next(i for i, (pr, _) in enumerate(projs) if pr.can_fuse())
+            if len(projs) > 1:
+                prod.x_out_f16 = p(self.x_h)
+            projs[lead][0].launch_fused(p(acc_buf) + 4 * (acc_off + projs[lead][1]), prod, st)
+            for i, (proj, off) in enumerate(projs):
+                if i != lead:
+                    proj.launch(p(acc_buf) + 4 * (acc_off + off), p(self.x_h), st)
+
+        prev = None
+        for li, ly in enumerate(self.layers):
+            if prev is None:
+                prod = xp(hc, norm=ly["norm1"], su=ly["SU_qkv"])  # acc_qkv was cleared by the previous step's last exchange
+            else:
+                gather("acc_dn", 4 * (li - 1) + 3, self.acc_qkv)
+                prod = xp(hc, h_out=ho, acc=self.acc_dn, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"])
+            run_group(ly["qkv"], self.acc_qkv, 0, prod)
+            if prev is not None:
+                hc, ho = ho, hc
+            check(L.qp_rope_attention(p(self.attn) + 2 * rank * (H // world), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq),
+                                      p(ly["kc"]), p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
+                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
+            gather("attn", 4 * li + 0, self.acc_o)
+            run_group([(ly["o"], 0)], self.acc_o, rank * Ho, xp(self.attn, su=ly["SU_o"]))
+            gather("acc_o", 4 * li + 1, self.acc_ug)
+            run_group(ly["ug"], self.acc_ug, 0, xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"]))
+            hc, ho = ho, hc
+            xc = self.region.xchg("z", 4 * li + 2)
+            keep.append(xc)
+            check(L.qp_silu_mul_had_grid_xchg(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i,
+                                              p(self.acc_dn), self.acc_dn.numel(), p(self.sync), ctypes.byref(xc), st))
+            ly["down"].launch(p(self.acc_dn) + 4 * rank * Ho, p(self.x_i), st)
+            prev = ly
+        xc = self.region.xchg("acc_dn", 4 * (len(self.layers) - 1) + 3)
+        keep.append(xc)
+        check(L.qp_fused_norm_had_xchg(p(self.xf), p(hc), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
+                                       sh.rms_norm_eps, None, H, 1.0, 0, p(self.acc_qkv), self.acc_qkv.numel(),
+                                       ctypes.byref(xc), st))
+        check(L.qp_gemv_f16(p(self.logits), p(self.lm_head), p(self.xf), sh.vocab_size, H, st))
+        check(L.qp_argmax(p(self.token), p(self.logits), sh.vocab_size, p(self.scratch), st))
+        check(L.qp_step_advance(p(self.pos), p(self.history), p(self.token), self.max_seq, st))
+        self.launches_per_step = _cabi.launch_count() - n0
 
     def _step_fused(self):
         """one decode step with residual/RMSNorm/sign/Hadamard fused into the GEMV prologues: per layer 4 GEMVs +

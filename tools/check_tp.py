@@ -19,15 +19,17 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 from qpalette.decode import DecodeRunner, LLAMA31_8B, LlamaShape, uniform_qdict
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-TOL = 1e-3
+TOL = 2e-3  # whole-model logits: 2x the per-layer tolerance (run-to-run noise of the same launch list is 4e-4 .. 8e-4)
 
 
 def run(shape, qd, mi, mode, nl, steps=4, graph=False, fused=False, ref_fn=None):
     kw = dict(max_seq=64, seed=5, num_layers=nl)
     if mode == "single":
         r = DecodeRunner(shape, qd, mi, fused=fused, **kw)
-    else:
-        r = DecodeRunner(shape, qd, mi, rank=rank, world=world, process_group=dist.group.WORLD, p2p=(mode == "p2p"), **kw)
+    else:  # p2p: NVLink peer exchange + fused GEMV prologues; p2p_unfused: peer exchange inside the glue kernels; nccl: baseline
+        r = DecodeRunner(shape, qd, mi, rank=rank, world=world, process_group=dist.group.WORLD, p2p=mode.startswith("p2p"),
+                         fused=(mode == "p2p"), **kw)
+        assert r.fused == (mode == "p2p"), (mode, r.fused, r.p2p)
     r.reset(3)
     if graph:
         r.capture()
@@ -55,13 +57,13 @@ ok = True
 shape = LLAMA31_8B
 qd, mi = uniform_qdict(shape, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge_ug"]] * 32
 ref_t, ref_l, _, _ = run(shape, qd, mi, "single", layers)
-for mode, graph, fused in (("single", True, True), ("p2p", False, False), ("p2p", True, False), ("nccl", False, False),
-                           ("nccl", True, False)):
+for mode, graph, fused in (("single", True, True), ("p2p", False, False), ("p2p", True, False), ("p2p_unfused", False, False),
+                           ("p2p_unfused", True, False), ("nccl", False, False), ("nccl", True, False)):
     t, l, us, _ = run(shape, qd, mi, mode, layers, graph=graph, fused=fused)
     err = max(float((a - b).norm() / b.norm()) for a, b in zip(l, ref_l))
     good = t == ref_t and err <= TOL
     ok &= good
-    print(f"[rank {rank}] 8B x{layers} {mode:6s} graph={graph}: tokens {t} vs single {ref_t}  max rel-L2 of logits vs single "
+    print(f"[rank {rank}] 8B x{layers} {mode:11s} graph={graph}: tokens {t} vs single {ref_t}  max rel-L2 of logits vs single "
           f"{err:.2e}  {'' if us is None else f'{us:.1f} us/step'}  {'OK' if good else 'MISMATCH'}", flush=True)
 
 # ---- small model against the oracle restatement ------------------------------------------------------------------------
@@ -75,9 +77,9 @@ sqd, smi = uniform_qdict(small, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge
 single = DecodeRunner(small, sqd, smi, max_seq=64, seed=5, fused=False)   # same seed -> same full-width weights: the oracle side
 caches = [([], []) for _ in single.layers]
 tok, refs = 3, []
-for mode in ("p2p", "nccl"):
+for mode in ("p2p", "p2p_unfused", "nccl"):
     r = DecodeRunner(small, sqd, smi, max_seq=64, seed=5, rank=rank, world=world, process_group=dist.group.WORLD,
-                     p2p=(mode == "p2p"))
+                     p2p=mode.startswith("p2p"), fused=(mode == "p2p"))
     r.reset(3)
     tok = 3
     for step in range(3):
@@ -89,7 +91,7 @@ for mode in ("p2p", "nccl"):
         err = float(np.linalg.norm(lg - refs[step]) / np.linalg.norm(refs[step]))
         good = err <= TOL and int(r.token.item()) == int(np.argmax(refs[step]))
         ok &= good
-        print(f"[rank {rank}] small {mode:5s} step {step}: rel-L2 of logits vs oracle restatement {err:.2e} "
+        print(f"[rank {rank}] small {mode:11s} step {step}: rel-L2 of logits vs oracle restatement {err:.2e} "
               f"{'OK' if good else 'MISMATCH'}", flush=True)
         tok = int(r.token.item())
 dist.barrier(); torch.cuda.synchronize()
