@@ -370,6 +370,226 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
     if (n > 0 && kleft != seg.ksuper) gemv2_flush(out, M, bs, row, acc);
 }
 
+// =====================================================================================================================
+// Batched form of the same loop for 9 <= bs <= 32 (NB = 2 or 4 blocks of 8 batch rows): a super-tile is decoded ONCE and fed to
+// 4 * NB mma.  The reference dequantises the whole matrix to HBM and calls cuBLAS there (lib/linear/tcq_linear.py:75-84); the
+// tcgen05 kernel of gemm_tc_kernels.cu is decode-latency bound (18 warps, 30 us at 14336x4096) and stays for bs > 32.
+// x (bs, K) does not fit next to the 128 KiB codebook (and re-reading its fragments from L2 per super-tile is 58-117 MB of L2
+// traffic at 14336x4096, which is what bounded the first version), so the work is ordered K-SLAB major: a slab is
+// kMmaSlabBytes of x in fragment order = W = 128 / NB super-tile columns; the flat work index runs over
+// [part][slab][strip][column in slab], every CTA takes an equal contiguous range of it (1-2 slabs), stages the slab's
+// fragments in shared memory once and its 24 warps split the range evenly.  Inside a slab a strip's W super-tiles are
+// contiguous in memory and the next strip is a constant jump away; the C fragments of a (strip, slab) go to `out` with fp32
+// atomics (32 * bs floats per W super-tiles: < 0.3 M sector atomics per launch).
+// =====================================================================================================================
+constexpr int kMmaSlabBytes = 64 * 1024;
+// payload ring depth of the batched loop
+#ifndef QP_MMA_DEPTH4
+#define QP_MMA_DEPTH4 3
+#endif
+template <int NB>
+constexpr int kMmaDepth = NB >= 4 ? QP_MMA_DEPTH4 : kGemv2Depth;
+
+// x (bs, K) fp16 -> fragment order xfrag[kh][j][lane] (uint4; j = batch block, lane = (n % 8) * 4 + q); rows past bs are zero
+static __global__ void x_to_frag_kernel(uint4 *__restrict__ xfrag, const uint32_t *x32, int K, int bs, int NB) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int total = (K / 32) * NB * 32;
+    const int kw = K / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int lane = i & 31, j = (i >> 5) % NB, kh = (i >> 5) / NB;
+        const int n = j * 8 + (lane >> 2), q = lane & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (n < bs) {
+            const uint32_t *src = x32 + (size_t)n * kw + kh * 16 + q;
+            v = make_uint4(__ldcg(src), __ldcg(src + 4), __ldcg(src + 8), __ldcg(src + 12));
+        }
+        xfrag[i] = v;
+    }
+}
+
+// one CTA-uniform piece of work: the part of the CTA's flat range that lies in one slab
+struct MmaPiece {
+    int part;        // 0 / 1
+    int col0, w;     // first super-tile column of the slab inside the part, slab width
+    unsigned lo, n;  // first index inside the slab ([strip][column in slab]) and count
+    unsigned next;   // flat index after this piece
+};
+// flat order: part A slabs, then part B slabs; all slabs of a part are W wide except its last
+__device__ __forceinline__ MmaPiece mma_piece(const PackSegment a, const PackSegment b, int W, unsigned lo, unsigned hi) {
+    const unsigned TA = (unsigned)a.strips * (unsigned)a.ksuper;
+    MmaPiece pc;
+    pc.part = lo >= TA;
+    const PackSegment s = pc.part ? b : a;
+    const unsigned rel = lo - (pc.part ? TA : 0u), full = (unsigned)s.strips * (unsigned)W;
+    const int ns = (s.ksuper + W - 1) / W;
+    int j = (int)(rel / full);
+    if (j > ns - 1) j = ns - 1;
+    pc.col0 = j * W;
+    pc.w = min(W, s.ksuper - pc.col0);
+    pc.lo = rel - (unsigned)j * full;
+    const unsigned slab_n = (unsigned)s.strips * (unsigned)pc.w;
+    pc.n = min(hi - lo, slab_n - pc.lo);
+    pc.next = lo + pc.n;
+    return pc;
+}
+
+// a warp's share of a piece: payload pointer of the prefetch stream, countdowns of both streams
+struct MmaRun {
+    const uint32_t *p;  // next payload to fetch (lane pointer)
+    int pleft;          // fetches until the prefetch stream leaves its strip
+    int kleft;          // steps until the consume stream leaves its strip
+    int row;            // output row of the consume stream's strip
+    int n;              // super-tiles of this warp
+    uint32_t xoff;      // byte offset of the consume stream's x fragments inside the slab
+};
+
+template <int E>
+__device__ __forceinline__ void mma_fetch(MmaRun &r, uint32_t (&raw)[TcqGeom<E>::kRawWords], bool pred, int w, int jump_words) {
+    pack_load_raw_pred<E>(raw, r.p, pred);
+    r.p += TcqGeom<E>::kSuperBytes / 4;
+    if (--r.pleft == 0) {
+        r.p += jump_words;
+        r.pleft = w;
+    }
+}
+
+template <int E, int NB>
+__device__ __forceinline__ MmaRun mma_begin(const PackSegment seg, const MmaPiece pc, int warps,
+                                            uint32_t (&raw)[kMmaDepth<NB>][TcqGeom<E>::kRawWords]) {
+    using G = TcqGeom<E>;
+    const unsigned wi = (unsigned)warp_in_cta();
+    const unsigned lo = pc.lo + (unsigned)(((unsigned long long)pc.n * wi) / (unsigned)warps);
+    const unsigned hi = pc.lo + (unsigned)(((unsigned long long)pc.n * (wi + 1)) / (unsigned)warps);
+    const int mh = (int)(lo / (unsigned)pc.w), kw = (int)(lo - (unsigned)mh * (unsigned)pc.w);
+    int word0, bitoff;
+    tcq_lane_addr<E>(threadIdx.x & 31, word0, bitoff);
+    MmaRun r;
+    r.p = seg.codes + word0 + ((size_t)mh * seg.ksuper + pc.col0 + kw) * (G::kSuperBytes / 4);
+    r.pleft = r.kleft = pc.w - kw;
+    r.row = seg.row0 + mh * 32;
+    r.n = (int)(hi - lo);
+    r.xoff = ((uint32_t)kw * (NB * 32) + (threadIdx.x & 31)) * 16u;
+    const int jump = (seg.ksuper - pc.w) * (G::kSuperBytes / 4);
+#pragma unroll
+    for (int d = 0; d < kMmaDepth<NB>; ++d) {
+#pragma unroll
+        for (int i = 0; i < G::kRawWords; ++i) raw[d][i] = 0u;
+        mma_fetch<E>(r, raw[d], d < r.n, pc.w, jump);
+    }
+    return r;
+}
+
+template <int NB>
+__device__ __forceinline__ void mma_flush(float *__restrict__ out, int M, int bs, int row, float (&acc)[NB][2][4]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const int c0 = j * 8 + 2 * (lane & 3);
+        float *a = out + (size_t)c0 * M + row + (lane >> 2);
+        if (c0 < bs) {
+            atomicAdd(a, acc[j][0][0]);
+            atomicAdd(a + 8, acc[j][0][2]);
+            atomicAdd(a + 16, acc[j][1][0]);
+            atomicAdd(a + 24, acc[j][1][2]);
+        }
+        if (c0 + 1 < bs) {
+            a += M;
+            atomicAdd(a, acc[j][0][1]);
+            atomicAdd(a + 8, acc[j][0][3]);
+            atomicAdd(a + 16, acc[j][1][1]);
+            atomicAdd(a + 24, acc[j][1][3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j][i][k] = 0.f;
+    }
+}
+
+template <class Dec, int NB>
+__device__ __forceinline__ void mma_consume(const uint32_t (&P)[TcqGeom<Dec::kE>::kWords], uint32_t xaddr, int lane,
+                                            uint32_t tab_lane, float (&acc)[NB][2][4]) {
+    uint32_t frag[4][4];  // [tile = kl*2+ml][register]
+    Dec::decode(P, lane, tab_lane, frag);
+    if constexpr (NB <= 2) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const uint4 xb = lds_u128(xaddr + j * 512);
+            mma_16816(acc[j][0], frag[0][0], frag[0][1], frag[0][2], frag[0][3], xb.x, xb.y);
+            mma_16816(acc[j][1], frag[1][0], frag[1][1], frag[1][2], frag[1][3], xb.x, xb.y);
+            mma_16816(acc[j][0], frag[2][0], frag[2][1], frag[2][2], frag[2][3], xb.z, xb.w);
+            mma_16816(acc[j][1], frag[3][0], frag[3][1], frag[3][2], frag[3][3], xb.z, xb.w);
+        }
+    } else {  // registers to spare (512 threads): all x fragments first, the two mma of an accumulator 2 * NB instructions apart
+        uint4 xb[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) xb[j] = lds_u128(xaddr + j * 512);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            mma_16816(acc[j][0], frag[0][0], frag[0][1], frag[0][2], frag[0][3], xb[j].x, xb[j].y);
+            mma_16816(acc[j][1], frag[1][0], frag[1][1], frag[1][2], frag[1][3], xb[j].x, xb[j].y);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            mma_16816(acc[j][0], frag[2][0], frag[2][1], frag[2][2], frag[2][3], xb[j].z, xb[j].w);
+            mma_16816(acc[j][1], frag[3][0], frag[3][1], frag[3][2], frag[3][3], xb[j].z, xb[j].w);
+        }
+    }
+}
+
+// stream a warp's share of one piece; xs_addr = shared-memory address of the staged slab
+template <class Dec, int NB>
+__device__ __forceinline__ void mma_stream(const PackSegment seg, const MmaPiece pc, MmaRun r, float *__restrict__ out, int M,
+                                           int bs, uint32_t xs_addr, uint32_t tab_lane,
+                                           uint32_t (&raw)[kMmaDepth<NB>][TcqGeom<Dec::kE>::kRawWords]) {
+    constexpr int E = Dec::kE, D = kMmaDepth<NB>;
+    using G = TcqGeom<E>;
+    const int lane = threadIdx.x & 31;
+    const int bitoff = (lane * G::kLaneBytes & 3) * 8;
+    const int jump = (seg.ksuper - pc.w) * (G::kSuperBytes / 4);
+    const uint32_t xlane = xs_addr + (uint32_t)lane * 16u;
+    uint32_t xa = xs_addr + r.xoff;
+    float acc[NB][2][4];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j][i][k] = 0.f;
+    auto advance = [&]() {
+        xa += NB * 512;
+        if (--r.kleft == 0) {
+            mma_flush<NB>(out, M, bs, r.row, acc);
+            r.row += 32;
+            r.kleft = pc.w;
+            xa = xlane;
+        }
+    };
+    const int n = r.n;
+    int i = 0;
+    for (; i + D <= n; i += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            uint32_t P[G::kWords];
+            tcq_align<E>(raw[d], bitoff, P);
+            mma_fetch<E>(r, raw[d], i + d + D < n, pc.w, jump);
+            mma_consume<Dec, NB>(P, xa, lane, tab_lane, acc);
+            advance();
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) {
+        if (i + d < n) {
+            uint32_t P[G::kWords];
+            tcq_align<E>(raw[d], bitoff, P);
+            mma_consume<Dec, NB>(P, xa, lane, tab_lane, acc);
+            advance();
+        }
+    }
+    if (n > 0 && r.kleft != pc.w) mma_flush<NB>(out, M, bs, r.row, acc);
+}
+
 inline int check_align(const void *p, size_t a, const char *name) {
     if (((uintptr_t)p) % a != 0) return fail(QP_ERR_ALIGN, "%s must be %zu-byte aligned", name, a);
     return QP_OK;

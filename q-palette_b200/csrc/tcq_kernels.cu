@@ -64,39 +64,39 @@ struct TcqTable {
 // lane-replicated codebook straight from global memory, in two halves so that the kernels can put other work between
 // them: tcq_table_load issues all of a thread's tlut loads (one L2 round trip), tcq_table_store writes the copies.
 // A warp store covers 4 consecutive 128-byte slots (8 lanes x 16 bytes each).
-template <int S>
+template <int S, int WARPS = kGemvWarps>
 struct TcqTableRegs {
     static constexpr int kRows = TcqTable<S>::kBytes / 128;  // 128-byte rows of the table
-    static constexpr int kIter = (kRows + kGemvWarps * 4 - 1) / (kGemvWarps * 4);
+    static constexpr int kIter = (kRows + WARPS * 4 - 1) / (WARPS * 4);
     uint32_t v[kIter];
 };
 
-template <int S>
-__device__ __forceinline__ void tcq_table_load(TcqTableRegs<S> &t, const uint32_t *__restrict__ tlut) {
+template <int S, int WARPS = kGemvWarps>
+__device__ __forceinline__ void tcq_table_load(TcqTableRegs<S, WARPS> &t, const uint32_t *__restrict__ tlut) {
     using T = TcqTable<S>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
-        const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
+    for (int it = 0; it < TcqTableRegs<S, WARPS>::kIter; ++it) {
+        const int r = (it * WARPS + warp) * 4 + (lane >> 3);
         // 128-byte row r holds 128 >> kStrideLog2 entries; this lane's 16-byte chunk belongs to entry ef (incl. the fold bit)
         const int ef = (r << (7 - T::kStrideLog2)) + ((lane & 7) >> (T::kStrideLog2 - 4));
-        t.v[it] = (r < TcqTableRegs<S>::kRows) ? __ldg(tlut + (ef & ((1 << S) - 1))) : 0u;
+        t.v[it] = (r < TcqTableRegs<S, WARPS>::kRows) ? __ldg(tlut + (ef & ((1 << S) - 1))) : 0u;
     }
 }
 
 // the sign fold (negate component 0 for the upper half of the folded table) is applied here, at store time: nothing between
 // the load issue and this point may depend on the loaded values, so that their L2 round trip overlaps the rest of the prologue
-template <int S>
-__device__ __forceinline__ void tcq_table_store(uint32_t *tab, const TcqTableRegs<S> &t) {
+template <int S, int WARPS = kGemvWarps>
+__device__ __forceinline__ void tcq_table_store(uint32_t *tab, const TcqTableRegs<S, WARPS> &t) {
     using T = TcqTable<S>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll
-    for (int it = 0; it < TcqTableRegs<S>::kIter; ++it) {
-        const int r = (it * kGemvWarps + warp) * 4 + (lane >> 3);
+    for (int it = 0; it < TcqTableRegs<S, WARPS>::kIter; ++it) {
+        const int r = (it * WARPS + warp) * 4 + (lane >> 3);
         const int ef = (r << (7 - T::kStrideLog2)) + ((lane & 7) >> (T::kStrideLog2 - 4));
         const uint32_t v = (T::kFold && (ef >> S)) ? (t.v[it] ^ 0x8000u) : t.v[it];
-        if (r < TcqTableRegs<S>::kRows) t4[r * 8 + (lane & 7)] = make_uint4(v, v, v, v);
+        if (r < TcqTableRegs<S, WARPS>::kRows) t4[r * 8 + (lane & 7)] = make_uint4(v, v, v, v);
     }
 }
 
@@ -222,6 +222,65 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     __syncthreads();
     QP_PHASE(6);  // whole CTA done
 #endif
+}
+
+// ---- batched GEMM on the GEMV loop (9 <= bs <= 32 per launch) ------------------------------------------------------------
+#ifndef QP_MMA_THREADS4
+#define QP_MMA_THREADS4 512
+#endif
+// NB = 4 holds 32 accumulators: 16 warps of <= 128 registers instead of 24 of 80, which spilled inside the loop (measured
+// 14336x4096 bs = 32: 24.0 us at 512 threads, 25.0 at 640, 26.7 at 768 with a 2-deep ring).  NB = 8 (12 warps of 168
+// registers) measured 33-35 us for bs = 48 / 64 against 31-32 us of the tcgen05 kernel, so the mma form stops at bs = 32.
+template <int NB>
+constexpr int kMmaThreads = NB >= 4 ? QP_MMA_THREADS4 : kTcqThreads;
+// batch rows per launch -> blocks of 8 batch rows the kernel carries
+static inline int mma_batch_blocks(int bs) { return bs <= 16 ? 2 : 4; }
+constexpr int kMmaMaxBatch = 32;
+
+template <int KVA, int KVB, int S, int NB>
+__global__ void __launch_bounds__(kMmaThreads<NB>, 1)
+tcq_gemm_mma_kernel(TcqSegment segA, TcqSegment segB, RunSplit split, float *__restrict__ out, const uint4 *xfrag,
+                    const uint32_t *__restrict__ tlut, int M, int bs) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    uint4 *xs = reinterpret_cast<uint4 *>(smem + TcqTable<S>::kBytes);
+    constexpr int W = kMmaSlabBytes / (NB * 512), kWarps = kMmaThreads<NB> / 32;
+    const int lane = threadIdx.x & 31;
+    unsigned lo, hi;
+    split_range(split, (int)blockIdx.x, lo, hi);  // this CTA's range of the slab-major work order
+    if (lo >= hi) return;
+    uint32_t rawA[kMmaDepth<NB>][TcqGeom<KVA>::kRawWords];
+    uint32_t rawB[kMmaDepth<NB>][TcqGeom<KVB == 0 ? KVA : KVB>::kRawWords];
+    MmaPiece pc = mma_piece(segA, segB, W, lo, hi);
+    MmaRun run;
+    auto begin = [&]() {
+        if (KVB == 0 || pc.part == 0) run = mma_begin<KVA, NB>(segA, pc, kWarps, rawA);
+        else run = mma_begin<(KVB == 0 ? KVA : KVB), NB>(segB, pc, kWarps, rawB);
+    };
+    begin();  // the first payload loads are in flight while the codebook is built
+    TcqTableRegs<S, kWarps> tregs;
+    tcq_table_load<S, kWarps>(tregs, tlut);
+    tcq_table_store<S, kWarps>(tab, tregs);
+    pdl_wait();  // xfrag (and out) are produced by the preceding kernels
+    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;
+    const uint32_t xs_addr = smem_u32(xs);
+    while (true) {
+        {   // stage the slab's x fragments
+            const PackSegment sg = (KVB == 0 || pc.part == 0) ? segA : segB;
+            const uint4 *src = xfrag + (size_t)(sg.ksuper0 + pc.col0) * (NB * 32);
+            for (int i = threadIdx.x; i < pc.w * NB * 32; i += kMmaThreads<NB>) xs[i] = __ldcg(src + i);
+        }
+        __syncthreads();
+        if (KVB == 0 || pc.part == 0)
+            mma_stream<TcqDecoder<KVA, S>, NB>(segA, pc, run, out, M, bs, xs_addr, tab_addr_lane, rawA);
+        else
+            mma_stream<TcqDecoder<(KVB == 0 ? KVA : KVB), S>, NB>(segB, pc, run, out, M, bs, xs_addr, tab_addr_lane, rawB);
+        if (pc.next >= hi) break;
+        pc = mma_piece(segA, segB, W, pc.next, hi);
+        begin();
+        __syncthreads();  // every warp is done with the slab before it is overwritten
+    }
+    pdl_launch_dependents();
 }
 
 // ---- dequantise -----------------------------------------------------------------------------------------------------
@@ -374,6 +433,41 @@ static int dispatch_gemv(const TcqLaunch &L, int S, float *out, const void *x, c
 #endif
 }
 
+template <int KVA, int KVB, int S>
+static int launch_gemm_mma(const TcqLaunch &L, float *out, const uint4 *xfrag, const void *tlut, int M, int bs, cudaStream_t st) {
+    const int NB = mma_batch_blocks(bs), v = NB == 4;
+    auto kern = v == 0 ? tcq_gemm_mma_kernel<KVA, KVB, S, 2> : tcq_gemm_mma_kernel<KVA, KVB, S, 4>;
+    const int threads = v == 0 ? kMmaThreads<2> : kMmaThreads<4>;
+    static DeviceOnce configured[2];
+    if (configured[v].first()) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
+    }
+    const int nctas = sm_count();
+    const long T = (long)L.a.strips * L.a.ksuper + (long)L.b.strips * L.b.ksuper;
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(threads), (size_t)TcqTable<S>::kBytes + kMmaSlabBytes, st, L.a, L.b,
+                       make_split(T, nctas), out, xfrag, (const uint32_t *)tlut, M, bs));
+    return check_launch("tcq_gemm_mma");
+}
+
+// the reference pairs tlut_bits with the rate (9 up to KV = 8, else KV + 1: lib/utils/mem_op.py get_quant_info); other
+// combinations fall back to the tcgen05 / dequantise paths on the host side
+static int dispatch_gemm_mma(const TcqLaunch &L, int S, float *out, const uint4 *xfrag, const void *tlut, int M, int bs,
+                             cudaStream_t st) {
+#define QP_MMA1(KV, SS) \
+    if (L.kvb == 0 && L.kva == KV && S == SS) return launch_gemm_mma<KV, 0, SS>(L, out, xfrag, tlut, M, bs, st);
+#define QP_MMA2(KA, SS) \
+    if (L.kva == KA && L.kvb == KA + 1 && S == SS) return launch_gemm_mma<KA, KA + 1, SS>(L, out, xfrag, tlut, M, bs, st);
+#ifdef QP_FAST_BUILD
+    QP_MMA2(6, 9)
+#else
+    QP_MMA1(2, 9) QP_MMA1(3, 9) QP_MMA1(4, 9) QP_MMA1(5, 9) QP_MMA1(6, 9) QP_MMA1(7, 9) QP_MMA1(8, 9) QP_MMA1(9, 10) QP_MMA1(10, 11)
+    QP_MMA2(2, 9) QP_MMA2(3, 9) QP_MMA2(4, 9) QP_MMA2(5, 9) QP_MMA2(6, 9) QP_MMA2(7, 9) QP_MMA2(8, 10) QP_MMA2(9, 11)
+#endif
+#undef QP_MMA1
+#undef QP_MMA2
+    return fail(QP_ERR_ARG, "no mma GEMM instantiation for S=%d KV=(%d,%d)", S, L.kva, L.kvb);
+}
+
 static int dispatch_dequant(const TcqLaunch &L, int S, __half *W, const void *tlut, int K, cudaStream_t st) {
     if (L.kvb == 0) {
         switch (L.kva) {
@@ -455,6 +549,43 @@ extern "C" int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *cod
     int rc = qp_tcq_gemv(out_dev, codes1, codes2, x_dev, tlut_f16, M, K, bs, S, KV1, KV2, split_mode, part1, 0, stream);
     if (rc != QP_OK) return rc;
     QP_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)bs * M * 4, cudaMemcpyDeviceToHost, st));
+    return QP_OK;
+}
+
+// scratch bytes for the fragment-ordered copy of x (per launch of <= kMmaMaxBatch batch rows)
+static size_t gemm_mma_scratch_bytes(int K, int bs) { return (size_t)(K / 32) * mma_batch_blocks(bs) * 32 * 16; }
+
+extern "C" size_t qp_gemm_mma_scratch_bytes(int K, int bs) {
+    size_t total = 0;
+    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) total += gemm_mma_scratch_bytes(K, bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch);
+    return total;
+}
+
+extern "C" int qp_tcq_gemm_mma(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16,
+                               void *scratch, int M, int K, int bs, int S, int KV1, int KV2, int split_mode, int part1,
+                               unsigned flags, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out && x_f16 && tlut_f16 && scratch, "NULL pointer argument");
+    QP_CHECK_ARG(bs >= 1 && bs <= 128, "bs = %d out of range 1..128", bs);
+    TcqLaunch L;
+    int rc = make_segments(L, codes1, codes2, M, K, KV1, KV2, split_mode, part1);
+    if (rc != QP_OK) return rc;
+    if ((rc = check_align(codes1, 16, "codes1")) != QP_OK) return rc;
+    if (codes2 && (rc = check_align(codes2, 16, "codes2")) != QP_OK) return rc;
+    if ((rc = check_align(x_f16, 4, "x")) != QP_OK) return rc;
+    if ((rc = check_align(scratch, 16, "scratch")) != QP_OK) return rc;
+    if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
+    uint8_t *sc = (uint8_t *)scratch;
+    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) {
+        const int nb = bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch, NB = mma_batch_blocks(nb);
+        const int total = (K / 32) * NB * 32;
+        QP_CUDA(launch_pdl(x_to_frag_kernel, dim3((total + 255) / 256), dim3(256), 0, st, (uint4 *)sc,
+                           (const uint32_t *)((const __half *)x_f16 + (size_t)b0 * K), K, nb, NB));
+        if ((rc = check_launch("x_to_frag")) != QP_OK) return rc;
+        rc = dispatch_gemm_mma(L, S, out + (size_t)b0 * M, (const uint4 *)sc, tlut_f16, M, nb, st);
+        if (rc != QP_OK) return rc;
+        sc += gemm_mma_scratch_bytes(K, nb);
+    }
     return QP_OK;
 }
 

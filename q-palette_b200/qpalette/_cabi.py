@@ -24,6 +24,8 @@ SIGNATURES = {
     "qp_tcq_gemv": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
     "qp_tcq_dequant": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "qp_tcq_gemm_tc": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
+    "qp_gemm_mma_scratch_bytes": [_i, _i],
+    "qp_tcq_gemm_mma": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_gemm_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -54,7 +56,7 @@ SIGNATURES = {
     "qp_lut_gemv_fused": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_tcq_gemv_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
-_RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64}
+_RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64, "qp_gemm_mma_scratch_bytes": ctypes.c_size_t}
 
 
 class XProd(ctypes.Structure):

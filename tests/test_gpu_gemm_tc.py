@@ -17,6 +17,13 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+@pytest.fixture(autouse=True)
+def tcgen05_only(monkeypatch):
+    """this file tests the tcgen05 kernel: keep small batches off the mma.sync path (tests/test_gpu_gemm_mma.py)"""
+    from qpalette import ops
+    monkeypatch.setattr(ops, "MMA_GEMM_MAX_BS", 0)
+
+
 def rand_tlut(rng, S):
     return (rng.standard_normal((1 << S, 2)) * 0.9).astype(np.float16)
 
