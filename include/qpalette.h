@@ -82,10 +82,13 @@ int qp_tcq_gemm_tc(float *out, const void *codes1, const void *codes2, const voi
  * GEMV's decode loop: a 32x32 super-tile is decoded once and multiplied with the whole batch by mma.sync (fp32 accumulate);
  * the work is ordered by K-slabs so that a CTA keeps its slab of x fragments in shared memory, and a finished (strip, slab)
  * is added to out with fp32 atomics.  Needs M % 32 == 0 and parts of K % 32 == 0 only.  `scratch`: device buffer of qp_gemm_mma_scratch_bytes(K, bs) bytes (a fragment-ordered copy of x is built there).
+ * qp_lut_gemm_mma: every VQ (vec_sz 2, 2..12 bits) and SQ (vec_sz 1, 2..8 bits) format of qp_lut_gemv.
  * TCQ: tlut_bits must be the reference's pairing for the rate (9 up to KV = 8, KV + 1 above; lib/utils/mem_op.py). */
 size_t qp_gemm_mma_scratch_bytes(int K, int bs);
 int qp_tcq_gemm_mma(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16, void *scratch,
                     int M, int K, int bs, int S, int KV1, int KV2, int split_mode, int part1, unsigned flags, void *stream);
+int qp_lut_gemm_mma(float *out, const void *codes, const void *x_f16, const void *lut_f16, void *scratch, int M, int K, int bs,
+                    int bits, int vec_sz, unsigned flags, void *stream);
 int qp_lut_gemm_tc(float *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs, int bits,
                    int vec_sz, unsigned flags, void *stream);
 

@@ -595,4 +595,40 @@ inline int check_align(const void *p, size_t a, const char *name) {
     return QP_OK;
 }
 
+// ---- host side of the batched mma form: <= kMmaMaxBatch batch rows per launch, fragment-ordered x in `scratch` ----
+#ifndef QP_MMA_THREADS4
+#define QP_MMA_THREADS4 512
+#endif
+// NB = 4 holds 32 accumulators: 16 warps of <= 128 registers instead of 24 of 80, which spilled inside the loop (measured
+// 14336x4096 bs = 32: 24.0 us at 512 threads, 25.0 at 640, 26.7 at 768 with a 2-deep ring).  NB = 8 (12 warps of 168
+// registers) measured 33-35 us for bs = 48 / 64 against 31-32 us of the tcgen05 kernel, so the mma form stops at bs = 32.
+template <int NB>
+constexpr int kMmaThreads = NB >= 4 ? QP_MMA_THREADS4 : kGemvThreads;
+// batch rows per launch -> blocks of 8 batch rows the kernel carries
+static inline int mma_batch_blocks(int bs) { return bs <= 16 ? 2 : 4; }
+constexpr int kMmaMaxBatch = 32;
+
+static inline size_t gemm_mma_scratch_bytes(int K, int bs) { return (size_t)(K / 32) * mma_batch_blocks(bs) * 32 * 16; }
+static inline size_t gemm_mma_scratch_total(int K, int bs) {
+    size_t total = 0;
+    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) total += gemm_mma_scratch_bytes(K, bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch);
+    return total;
+}
+// launch_one(out rows b0.., xfrag, nb) launches the GEMM kernel for one chunk of the batch
+template <class F>
+static int mma_gemm_batches(float *out, const void *x_f16, void *scratch, int M, int K, int bs, cudaStream_t st, F launch_one) {
+    uint8_t *sc = (uint8_t *)scratch;
+    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) {
+        const int nb = bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch, NB = mma_batch_blocks(nb);
+        const int total = (K / 32) * NB * 32;
+        QP_CUDA(launch_pdl(x_to_frag_kernel, dim3((total + 255) / 256), dim3(256), 0, st, (uint4 *)sc,
+                           (const uint32_t *)((const __half *)x_f16 + (size_t)b0 * K), K, nb, NB));
+        int rc = check_launch("x_to_frag");
+        if (rc != QP_OK) return rc;
+        if ((rc = launch_one(out + (size_t)b0 * M, (const uint4 *)sc, nb)) != QP_OK) return rc;
+        sc += gemm_mma_scratch_bytes(K, nb);
+    }
+    return QP_OK;
+}
+
 }  // namespace qp

@@ -106,6 +106,45 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     gemv2_run<LutDecoder<E, SPLIT>>(seg, out, M, bs, smem_u32(xs), tab_addr_lane, run, raw, [] {});
 }
 
+// batched form for 9 <= bs <= 32 (see gemv_common.cuh: K-slabs of x fragments in shared memory, NB blocks of 8 batch rows);
+// replaces `decompress_* + x @ dq.T` of lib/linear/vq_linear.py:58-66 at these batch sizes
+template <int E, bool SPLIT, int NB>
+__global__ void __launch_bounds__(kMmaThreads<NB>, 1)
+lut_gemm_mma_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const uint4 *xfrag, const void *__restrict__ lut,
+                    int r_single, int M, int bs) {
+    using T = LutTable<E, SPLIT>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);  // compact lut copy
+    uint4 *xs = reinterpret_cast<uint4 *>(lc + lut_compact_words(E, r_single));
+    constexpr int W = kMmaSlabBytes / (NB * 512), kWarps = kMmaThreads<NB> / 32;
+    const int lane = threadIdx.x & 31;
+    unsigned lo, hi;
+    split_range(split, (int)blockIdx.x, lo, hi);
+    if (lo >= hi) return;
+    const PackSegment none{nullptr, 0, 0, 0, 0};
+    uint32_t raw[kMmaDepth<NB>][TcqGeom<E>::kRawWords];
+    MmaPiece pc = mma_piece(seg, none, W, lo, hi);
+    MmaRun run = mma_begin<E, NB>(seg, pc, kWarps, raw);
+    coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
+    __syncthreads();
+    lut_build_table<E, SPLIT>(tab, lc, r_single);
+    pdl_wait();
+    const uint32_t tab_addr_lane = (lane & T::kLaneMask) << 2;
+    const uint32_t xs_addr = smem_u32(xs);
+    while (true) {
+        const uint4 *src = xfrag + (size_t)(seg.ksuper0 + pc.col0) * (NB * 32);
+        for (int i = threadIdx.x; i < pc.w * NB * 32; i += kMmaThreads<NB>) xs[i] = __ldcg(src + i);
+        __syncthreads();
+        mma_stream<LutDecoder<E, SPLIT>, NB>(seg, pc, run, out, M, bs, xs_addr, tab_addr_lane, raw);
+        if (pc.next >= hi) break;
+        pc = mma_piece(seg, none, W, pc.next, hi);
+        run = mma_begin<E, NB>(seg, pc, kWarps, raw);
+        __syncthreads();
+    }
+    pdl_launch_dependents();
+}
+
 template <int E, bool SPLIT>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 lut_dequant_kernel(PackSegment seg, RunSplit split, __half *__restrict__ W, const void *__restrict__ lut, int r_single,
@@ -140,6 +179,23 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
                        make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), out, (const uint32_t *)x, lut,
                        r_single, M, K, bs, prod));
     return check_launch("lut_gemv");
+}
+
+template <int E, bool SPLIT>
+static int launch_lut_gemm_mma(PackSegment seg, float *out, const uint4 *xfrag, const void *lut, int r_single, int M, int bs,
+                               cudaStream_t st) {
+    using T = LutTable<E, SPLIT>;
+    const int v = mma_batch_blocks(bs) == 4;
+    auto kern = v == 0 ? lut_gemm_mma_kernel<E, SPLIT, 2> : lut_gemm_mma_kernel<E, SPLIT, 4>;
+    static DeviceOnce configured[2];
+    if (configured[v].first()) {
+        QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
+    }
+    const int nctas = sm_count();
+    const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + kMmaSlabBytes;
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(v == 0 ? kMmaThreads<2> : kMmaThreads<4>), smem, st, seg,
+                       make_split((long)seg.strips * seg.ksuper, nctas), out, xfrag, lut, r_single, M, bs));
+    return check_launch("lut_gemm_mma");
 }
 
 template <int E, bool SPLIT>
@@ -202,6 +258,13 @@ static int dispatch_lut_gemv(int bits, int vec_sz, PackSegment seg, float *out, 
     return fail(QP_ERR_ARG, "unsupported LUT configuration bits=%d vec_sz=%d", bits, vec_sz);
 }
 
+static int dispatch_lut_gemm_mma(int bits, int vec_sz, PackSegment seg, float *out, const uint4 *xfrag, const void *lut, int M,
+                                 int bs, cudaStream_t st) {
+    const int r_single = vec_sz == 1 ? bits : 0;
+    QP_LUT_DISPATCH(launch_lut_gemm_mma, seg, out, xfrag, lut, r_single, M, bs, st)
+    return fail(QP_ERR_ARG, "unsupported LUT configuration bits=%d vec_sz=%d", bits, vec_sz);
+}
+
 static int dispatch_lut_dequant(int bits, int vec_sz, PackSegment seg, __half *W, const void *lut, int K,
                                 cudaStream_t st) {
     const int r_single = vec_sz == 1 ? bits : 0;
@@ -243,6 +306,22 @@ extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, con
         if (rc != QP_OK) return rc;
     }
     return QP_OK;
+}
+
+extern "C" int qp_lut_gemm_mma(float *out, const void *codes, const void *x_f16, const void *lut_f16, void *scratch, int M, int K,
+                               int bs, int bits, int vec_sz, unsigned flags, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    QP_CHECK_ARG(out && x_f16 && lut_f16 && scratch, "NULL pointer argument");
+    QP_CHECK_ARG(bs >= 1 && bs <= 128, "bs = %d out of range 1..128", bs);
+    int rc = lut_check(codes, M, K, bits, vec_sz);
+    if (rc != QP_OK) return rc;
+    if ((rc = check_align(x_f16, 4, "x")) != QP_OK) return rc;
+    if ((rc = check_align(scratch, 16, "scratch")) != QP_OK) return rc;
+    if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
+    PackSegment seg{(const uint32_t *)codes, M / 32, K / 32, 0, 0};
+    return mma_gemm_batches(out, x_f16, scratch, M, K, bs, st, [&](float *o, const uint4 *xfrag, int nb) {
+        return dispatch_lut_gemm_mma(bits, vec_sz, seg, o, xfrag, lut_f16, M, nb, st);
+    });
 }
 
 extern "C" int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f16, int M, int K, int bits, int vec_sz,

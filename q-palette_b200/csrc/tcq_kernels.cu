@@ -225,18 +225,6 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
 }
 
 // ---- batched GEMM on the GEMV loop (9 <= bs <= 32 per launch) ------------------------------------------------------------
-#ifndef QP_MMA_THREADS4
-#define QP_MMA_THREADS4 512
-#endif
-// NB = 4 holds 32 accumulators: 16 warps of <= 128 registers instead of 24 of 80, which spilled inside the loop (measured
-// 14336x4096 bs = 32: 24.0 us at 512 threads, 25.0 at 640, 26.7 at 768 with a 2-deep ring).  NB = 8 (12 warps of 168
-// registers) measured 33-35 us for bs = 48 / 64 against 31-32 us of the tcgen05 kernel, so the mma form stops at bs = 32.
-template <int NB>
-constexpr int kMmaThreads = NB >= 4 ? QP_MMA_THREADS4 : kTcqThreads;
-// batch rows per launch -> blocks of 8 batch rows the kernel carries
-static inline int mma_batch_blocks(int bs) { return bs <= 16 ? 2 : 4; }
-constexpr int kMmaMaxBatch = 32;
-
 template <int KVA, int KVB, int S, int NB>
 __global__ void __launch_bounds__(kMmaThreads<NB>, 1)
 tcq_gemm_mma_kernel(TcqSegment segA, TcqSegment segB, RunSplit split, float *__restrict__ out, const uint4 *xfrag,
@@ -552,14 +540,7 @@ extern "C" int qp_tcq_gemv_host(float *out_host, float *out_dev, const void *cod
     return QP_OK;
 }
 
-// scratch bytes for the fragment-ordered copy of x (per launch of <= kMmaMaxBatch batch rows)
-static size_t gemm_mma_scratch_bytes(int K, int bs) { return (size_t)(K / 32) * mma_batch_blocks(bs) * 32 * 16; }
-
-extern "C" size_t qp_gemm_mma_scratch_bytes(int K, int bs) {
-    size_t total = 0;
-    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) total += gemm_mma_scratch_bytes(K, bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch);
-    return total;
-}
+extern "C" size_t qp_gemm_mma_scratch_bytes(int K, int bs) { return gemm_mma_scratch_total(K, bs); }
 
 extern "C" int qp_tcq_gemm_mma(float *out, const void *codes1, const void *codes2, const void *x_f16, const void *tlut_f16,
                                void *scratch, int M, int K, int bs, int S, int KV1, int KV2, int split_mode, int part1,
@@ -575,18 +556,9 @@ extern "C" int qp_tcq_gemm_mma(float *out, const void *codes1, const void *codes
     if ((rc = check_align(x_f16, 4, "x")) != QP_OK) return rc;
     if ((rc = check_align(scratch, 16, "scratch")) != QP_OK) return rc;
     if (!(flags & QP_FLAG_ACCUMULATE)) QP_CUDA(cudaMemsetAsync(out, 0, (size_t)bs * M * sizeof(float), st));
-    uint8_t *sc = (uint8_t *)scratch;
-    for (int b0 = 0; b0 < bs; b0 += kMmaMaxBatch) {
-        const int nb = bs - b0 < kMmaMaxBatch ? bs - b0 : kMmaMaxBatch, NB = mma_batch_blocks(nb);
-        const int total = (K / 32) * NB * 32;
-        QP_CUDA(launch_pdl(x_to_frag_kernel, dim3((total + 255) / 256), dim3(256), 0, st, (uint4 *)sc,
-                           (const uint32_t *)((const __half *)x_f16 + (size_t)b0 * K), K, nb, NB));
-        if ((rc = check_launch("x_to_frag")) != QP_OK) return rc;
-        rc = dispatch_gemm_mma(L, S, out + (size_t)b0 * M, (const uint4 *)sc, tlut_f16, M, nb, st);
-        if (rc != QP_OK) return rc;
-        sc += gemm_mma_scratch_bytes(K, nb);
-    }
-    return QP_OK;
+    return mma_gemm_batches(out, x_f16, scratch, M, K, bs, st, [&](float *o, const uint4 *xfrag, int nb) {
+        return dispatch_gemm_mma(L, S, o, xfrag, tlut_f16, M, nb, st);
+    });
 }
 
 #ifdef QP_PROFILE_PHASES

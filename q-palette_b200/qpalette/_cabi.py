@@ -27,6 +27,7 @@ SIGNATURES = {
     "qp_gemm_mma_scratch_bytes": [_i, _i],
     "qp_tcq_gemm_mma": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_gemm_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
+    "qp_lut_gemm_mma": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp],
     "qp_lut_dequant": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_simt_gemv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -38,7 +38,8 @@ class QTIPLinearTCQ(nn.Module):
         if bs <= 8:
             op = ops.resolve(f"decompress_gemm_tcq_{m}_{bs}_{k}_{self.tlut_bits}_{self.KV}")
             x = op(self.trellis, x, self.tlut)
-        elif ops.tc_gemm_supported(m, k):  # fused dequant + GEMM on tcgen05 (the reference: dequantise + cuBLAS)
+        elif ops.tc_gemm_supported(m, k) or (bs <= ops.MMA_GEMM_MAX_BS and ops._tcq_mma_supported(self.tlut_bits, self.KV, 0)):
+            # fused dequant + GEMM: mma.sync on the GEMV loop up to bs = 32, tcgen05 above (the reference: dequantise + cuBLAS)
             x = ops.tcq_gemm_tc(self.trellis, x, self.tlut, m, k, self.tlut_bits, self.KV)
         else:
             x = ops.batched_matmul(x, lambda: ops.resolve(f"decompress_tcq_{self.tlut_bits}_{self.KV}")(

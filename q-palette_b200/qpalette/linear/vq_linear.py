@@ -50,7 +50,9 @@ class VQLinearPackTensorCore(_VQBase):
         bs, m, k = x.shape[0], self.out_features, self.in_features
         if bs <= 8:
             x = ops.resolve(f"decompress_gemm_{m}_{bs}_{k}_{self.lut_bits}_{self.vq_type}")(self.qweight, x, self.lut)
-        elif ops.tc_gemm_supported(m, k) and (self.vec_sz == 2 or self.lut_bits <= 5):
+        elif bs <= ops.MMA_GEMM_MAX_BS:  # fused dequant + GEMM on the GEMV's decode loop, every format
+            x = ops.lut_gemm_mma(self.qweight, x, self.lut, m, k, self.lut_bits, self.vec_sz)
+        elif ops.tc_gemm_supported(m, k) and (self.vec_sz == 2 or self.lut_bits <= 5):  # ... on tcgen05
             x = ops.lut_gemm_tc(self.qweight, x, self.lut, m, k, self.lut_bits, self.vec_sz)
         else:
             x = ops.batched_matmul(x, lambda: ops.resolve(f"decompress_{self.lut_bits}_{self.vq_type}")(

@@ -104,3 +104,33 @@ def test_matches_gemv_and_tcgen05():
     c = torch.cat([ops.tcq_gemv(buf, x[i:i + 8], tl, M, K, S, KV) for i in (0, 8)])
     assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= TOL
     assert rel_l2(a.cpu().numpy(), c.float().cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("vec,R", [(2, 2), (2, 3), (2, 4), (2, 6), (2, 8), (2, 9), (2, 11), (2, 12), (1, 2), (1, 3), (1, 4), (1, 5),
+                                   (1, 6), (1, 7), (1, 8)])
+@pytest.mark.parametrize("bs", [9, 32])
+def test_lut_gemm_mma(vec, R, bs):
+    """VQ (vec_sz 2) and SQ (vec_sz 1, incl. the 6..8-bit split-lookup formats the tcgen05 kernel does not take)"""
+    from qpalette import ops
+    rng = np.random.default_rng(R * 2 + vec + bs)
+    M, K = 384, 1312  # 41 super-tile columns: a full slab + a narrow one at NB = 4
+    lut = rng.standard_normal((1 << R, vec)).astype(np.float16)
+    buf = rng.integers(0, 256, size=M * K * R // 8 // vec, dtype=np.uint8)
+    Wref = O.lut_tc_decode(buf.view(np.int32), lut, M, K, R, vec)
+    x = rng.standard_normal((bs, K)).astype(np.float16)
+    out = ops.lut_gemm_mma(cuda(buf), cuda(x), cuda(lut), M, K, R, vec).cpu().numpy()
+    assert rel_l2(out, O.gemv_ref(Wref, x)) <= TOL
+
+
+def test_lut_llama_shape_through_module_dispatch():
+    """ldlq_2_8 up_proj-sized layer at bs = 20 through the public dispatcher, accumulating"""
+    from qpalette import ops
+    rng = np.random.default_rng(3)
+    M, K, R, bs = 14336, 4096, 8, 20
+    lut = rng.standard_normal((1 << R, 2)).astype(np.float16)
+    buf = rng.integers(0, 256, size=M * K * R // 16, dtype=np.uint8)
+    Wref = O.lut_tc_decode(buf.view(np.int32), lut, M, K, R, 2)
+    x = rng.standard_normal((bs, K)).astype(np.float16)
+    base = rng.standard_normal((bs, M)).astype(np.float32)
+    out = ops.lut_gemm_tc(cuda(buf), cuda(x), cuda(lut), M, K, R, 2, out=cuda(base), accumulate=True).cpu().numpy()
+    assert rel_l2(out - base, O.gemv_ref(Wref, x)) <= TOL

@@ -42,3 +42,28 @@ for bs in (9, 16, 24, 32, 48, 64):
         print(f"14336x4096 tcomb_6_7 bs={bs:3d} {name:4s} {a.elapsed_time(b_) * 1e3 / 10 / len(bufs):7.2f} us", flush=True)
         if name == "tc":
             ops.MMA_GEMM_MAX_BS = saved
+# VQ sweep of BASELINE config 4 (ldlq_2_4 / 2_6 / 2_8) at the same shape
+for R in (4, 6, 8):
+    lut = torch.randn((1 << R, 2), device="cuda").half()
+    nbytes = M * K * R // 16
+    lbufs = [torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device="cuda") for _ in range(max(3, int(300e6 // nbytes)))]
+    for bs in (16, 32, 64):
+        x = torch.randn((bs, K), device="cuda").half()
+        out = torch.zeros((bs, M), dtype=torch.float32, device="cuda")
+        for name in ("mma", "tc"):
+            saved = ops.MMA_GEMM_MAX_BS
+            ops.MMA_GEMM_MAX_BS = 128 if name == "mma" else 0
+            run = lambda: [ops.lut_gemm_tc(b, x, lut, M, K, R, 2, out=out, accumulate=True) for b in lbufs]
+            run(); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            ops.MMA_GEMM_MAX_BS = saved
+            g.replay(); torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                g.replay()
+            b_.record(); torch.cuda.synchronize()
+            us = a.elapsed_time(b_) * 1e3 / 10 / len(lbufs)
+            print(f"14336x4096 ldlq_2_{R} bs={bs:3d} {name:4s} {us:7.2f} us  {nbytes / us / 1e3:7.1f} GB/s", flush=True)
