@@ -151,9 +151,14 @@ typedef struct qp_xchg {
 int qp_fused_norm_had_xchg(void *x_out_f16, void *h_f16, int h_writeback, const float *acc, const void *wscale_f16,
                            float acc_scale, const void *norm_w_f16, float eps, const void *su_f16, int n, float had_scale,
                            int do_had, float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
-/* The exchange of qp_fused_norm_had_xchg alone (clear zero_ptr, push own slice, wait for the peers'): for a consumer that is a
- * GEMV with the fused x-producer prologue (qp_*_gemv_fused), which then reads the completed buffer from the local region. */
-int qp_xchg_gather(float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream);
+/* Low-latency ("LL") gather for a consumer GEMV with a fused prologue (the row-sharded decode step uses it at the three
+ * sites in front of the qkv / o / up-gate projections): store this rank's slice (n elements;
+ * fp16, or fp32 accumulators converted to fp16) as {2 x fp16, epoch, 2 x fp16, epoch} entries into the buffer at xc->offset of
+ * EVERY rank's region (xc->slice_bytes = 4 * n per rank) and bump the site's epoch -- no fence, no flag, no wait.  The consumer
+ * (qp_*_gemv_fused with qp_xprod.ll = local region base + xc->offset, ll_epoch = xc->epoch + xc->site) polls the epoch of each
+ * entry it reads.  Clears zero_ptr[0..zero_count) first. */
+int qp_xchg_send_ll(const void *src_slice, int src_is_f32, int n, float *zero_ptr, int zero_count, const qp_xchg *xc,
+                    void *stream);
 /* Row-sharded SiLU*mul + Hadamard: acc_local / wscale_local = [up | gate] of this rank's I / nranks rows; one CTA per local
  * 512-element block pushes its transformed block into the exchange buffer at xc->offset (I floats) of every rank, then every
  * rank finishes the transform from its own copy: x_out = the complete fp16 vector on every rank.  *sync_counter: a local
@@ -220,6 +225,12 @@ typedef struct qp_xprod {
     int zero1_count;
     float *zero2;
     int zero2_count;
+    /* row-sharded mode (all NULL / 0 otherwise): one operand is polled out of the LL receive buffer qp_xchg_send_ll fills.
+     * ll_kind 1: the entries are fp16(acc) of the previous projection (acc must be NULL, wscale_f16 given);
+     * ll_kind 2: the entries are src (src_f16 is then ignored).  ll_epoch: the exchange site's epoch word. */
+    const void *ll;
+    const unsigned *ll_epoch;
+    int ll_kind;
 } qp_xprod;
 int qp_tcq_gemv_fused(float *out, const void *codes1, const void *codes2, const qp_xprod *xp, const void *tlut_f16,
                       int M, int K, int S, int KV1, int KV2, int split_mode, int part1, void *stream);

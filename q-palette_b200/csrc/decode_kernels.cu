@@ -249,16 +249,37 @@ fused_norm_had_kernel(__half *__restrict__ x_out, __half *h, int h_writeback, co
     }
 }
 
-// The exchange alone: complete a row-sharded buffer in place on every rank (push own slice to the peers, wait for theirs) and
-// clear `zero_ptr` first.  Used in front of a GEMV whose fused prologue (xprod.cuh) consumes the completed buffer: the
-// residual / RMSNorm / Hadamard work then runs in all of the GEMV's CTAs instead of one 1024-thread CTA.
+// Fire-and-forget half of the LL exchange (the other half is polled inside the consumer GEMV's prologue, xprod.cuh): store
+// this rank's slice of a gathered fp16 vector -- converted from the fp32 accumulators when `src_is_f32` -- as LL entries
+// {2 x fp16, epoch, 2 x fp16, epoch} into the receive buffer of EVERY rank (own included), then bump the site's epoch.
+// No fence, no flag, no wait: an 8-byte {data, epoch} store is a single NVLink write, the consumers check the epoch of every
+// entry they read.  A receive buffer is rewritten one layer later at the earliest, and a peer can only get there after it
+// has received this rank's contribution to the sites in between, i.e. after this rank's consumer kernel has completed.
 __global__ void __launch_bounds__(kDecThreads, 1)
-xchg_gather_kernel(float *__restrict__ zero_ptr, int zero_count, XchgDev xc) {
+xchg_send_ll_kernel(const void *__restrict__ src_slice, int src_is_f32, int n, float *__restrict__ zero_ptr, int zero_count,
+                    XchgDev xc) {
     pdl_wait();
     pdl_launch_dependents();
-    // clear first: a peer only pushes into the cleared buffer after it has seen this rank's flag of this site
     if (zero_ptr) zero_words4(zero_ptr, zero_count);
-    peer_allgather(xc);
+    const unsigned ep = *xc.epoch + 1u;
+    const size_t off = (size_t)xc.offset + (size_t)xc.rank * xc.slice_bytes;
+    for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+        uint2 h;
+        if (src_is_f32) {
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(src_slice) + i);
+            const float f[4] = {a.x, a.y, a.z, a.w};
+            h = pack4(f);
+        } else {
+            h = __ldcg(reinterpret_cast<const uint2 *>(src_slice) + i);
+        }
+        for (int q = 0; q < xc.nranks; ++q) {
+            const int peer = (xc.rank + q) % xc.nranks;
+            uint4 *dst = reinterpret_cast<uint4 *>(xc.peer_base[peer] + off) + i;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(h.x), "r"(ep), "r"(h.y), "r"(ep) : "memory");
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *xc.epoch = ep;
 }
 
 // acc = [up (I) | gate (I)] fp32 -> y = silu(gate)*up (fp16 rounding points as the reference graph) -> *su -> had -> x
@@ -1013,13 +1034,20 @@ static int make_xchg_dev(XchgDev &d, const qp_xchg *xc) {
     return QP_OK;
 }
 
-extern "C" int qp_xchg_gather(float *zero_ptr, int zero_count, const qp_xchg *xc, void *stream) {
+extern "C" int qp_xchg_send_ll(const void *src_slice, int src_is_f32, int n, float *zero_ptr, int zero_count, const qp_xchg *xc,
+                               void *stream) {
+    QP_CHECK_ARG(src_slice && xc, "NULL pointer argument");
+    QP_CHECK_ARG(n > 0 && n % 4 == 0, "slice of %d elements is not a multiple of 4", n);
+    QP_CHECK_ARG(xc->slice_bytes == n * 4, "LL slice is 4 bytes per element: slice_bytes = %d for n = %d", xc->slice_bytes, n);
     XchgDev d;
     int rc = make_xchg_dev(d, xc);
     if (rc != QP_OK) return rc;
-    QP_CUDA(launch_pdl(xchg_gather_kernel, dim3(1), dim3(kDecThreads), 0, (cudaStream_t)stream, zero_ptr, zero_count, d));
-    return check_launch("xchg_gather");
+    QP_CHECK_ARG(((uintptr_t)src_slice) % 16 == 0, "src_slice must be 16-byte aligned");
+    QP_CUDA(launch_pdl(xchg_send_ll_kernel, dim3(1), dim3(kDecThreads), 0, (cudaStream_t)stream, src_slice, src_is_f32, n, zero_ptr,
+                       zero_count, d));
+    return check_launch("xchg_send_ll");
 }
+
 
 // ---- exchange region management (CUDA IPC) -------------------------------------------------------------------------------
 extern "C" int qp_peer_alloc(void **ptr, size_t bytes) {
@@ -1215,11 +1243,17 @@ extern "C" int qp_step_advance(int *pos, int *history, const int *token, int max
 }
 
 /* limit of the in-kernel flag waits of the peer-exchange kernels on the CURRENT device; ms <= 0 disables the trap */
+static unsigned long long g_spin_limit_host = 120000000000ull;  // mirror of qp::g_spin_limit_cycles for descriptors built on the host
+namespace qp {
+unsigned long long qp_spin_limit_cycles_host() { return g_spin_limit_host; }
+}  // namespace qp
+
 extern "C" int qp_set_spin_timeout_ms(long long ms) {
     int dev = 0, khz = 0;
     QP_CUDA(cudaGetDevice(&dev));
     QP_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
     const unsigned long long cyc = ms <= 0 ? 0ull : (unsigned long long)ms * (unsigned long long)(khz > 0 ? khz : 2000000);
     QP_CUDA(cudaMemcpyToSymbol(qp::g_spin_limit_cycles, &cyc, sizeof(cyc)));
+    g_spin_limit_host = cyc;
     return QP_OK;
 }

@@ -79,7 +79,8 @@ struct LutDecoder {
     }
 };
 
-template <int E, bool SPLIT>
+// LL: the fused prologue polls one operand out of the row-sharded LL receive buffer (xprod.cuh); separate instantiation
+template <int E, bool SPLIT, bool LL>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const uint32_t *__restrict__ x32,
                 const void *__restrict__ lut, int r_single, int M, int K, int bs, XProd prod) {
@@ -99,7 +100,7 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     if (prod.mode != 0) xp_zero(prod);  // before the wait: see xprod.cuh
     pdl_wait();
     if (prod.mode == 0) stage_x(xs, x32, K, bs);
-    else produce_x_dispatch(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
+    else produce_x_dispatch<LL>(xs, reinterpret_cast<float *>(xs + (size_t)K * bs / 2), red, prod, K);
     __syncthreads();
     pdl_launch_dependents();
     const uint32_t tab_addr_lane = (lane & T::kLaneMask) << 2;  // the table starts the dynamic shared memory
@@ -167,9 +168,10 @@ template <int E, bool SPLIT>
 static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const void *lut, int r_single, int M, int K,
                            int bs, const XProd &prod, cudaStream_t st) {
     using T = LutTable<E, SPLIT>;
-    auto kern = lut_gemv_kernel<E, SPLIT>;
-    static DeviceOnce configured;
-    if (configured.first()) {
+    const bool ll = prod.mode == 2;
+    auto kern = ll ? lut_gemv_kernel<E, SPLIT, true> : lut_gemv_kernel<E, SPLIT, false>;
+    static DeviceOnce configured[2];
+    if (configured[ll].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
     }
     const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2 +
@@ -338,6 +340,8 @@ extern "C" int qp_lut_dequant(void *W_f16, const void *codes, const void *lut_f1
 int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
     QP_CHECK_ARG(u->src_f16 != nullptr, "xprod.src_f16 is NULL");
     QP_CHECK_ARG(!u->acc || u->wscale_f16, "xprod.acc given without wscale");
+    QP_CHECK_ARG(!u->ll || (u->ll_epoch && (u->ll_kind == 1 || u->ll_kind == 2)), "xprod.ll needs ll_epoch and ll_kind 1 or 2");
+    QP_CHECK_ARG(!u->ll || u->ll_kind != 1 || (u->wscale_f16 && !u->acc), "xprod.ll_kind 1 replaces acc and needs wscale");
     QP_CHECK_ARG(K % 128 == 0, "fused prologue needs K %% 128 == 0 (K = %d)", K);
     int Kf = 1, m = K;
     if ((K & (K - 1)) != 0) {
@@ -347,7 +351,7 @@ int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
     }
     QP_CHECK_ARG(m >= 128, "Hadamard block %d < 128", m);
     QP_CHECK_ARG(K <= 5 * 4 * kGemvThreads, "K = %d too large for the fused prologue", K);
-    p.mode = 1;
+    p.mode = u->ll ? 2 : 1;
     p.src = (const __half *)u->src_f16;
     p.h_out = (__half *)u->h_out_f16;
     p.acc = u->acc;
@@ -364,6 +368,10 @@ int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
     p.zero2_count = u->zero2_count;
     p.m = m;
     p.Kf = Kf;
+    p.ll = (const uint4 *)u->ll;
+    p.ll_epoch = u->ll_epoch;
+    p.ll_kind = u->ll ? u->ll_kind : 0;
+    p.ll_spin_cycles = qp_spin_limit_cycles_host();
     return QP_OK;
 }
 

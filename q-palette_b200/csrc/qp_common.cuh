@@ -22,6 +22,9 @@ int sm_count();                               // cached cudaDevAttrMultiProcesso
 
 // one-time, PER-DEVICE setup guard of a kernel instantiation: cudaFuncSetAttribute (the opt-in to > 48 KB of dynamic
 // shared memory) is a per-device property, and one process may drive several GPUs (`with torch.cuda.device(...)`).
+// spin limit of the peer-exchange waits in SM cycles (0 = forever); set by qp_set_spin_timeout_ms (decode_kernels.cu)
+unsigned long long qp_spin_limit_cycles_host();
+
 struct DeviceOnce {
     std::atomic<unsigned long long> done{0};
     bool first() {

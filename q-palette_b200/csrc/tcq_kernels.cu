@@ -154,9 +154,9 @@ struct TcqDecoder {
 using TcqSegment = PackSegment;
 
 // ---- GEMV -----------------------------------------------------------------------------------------------------------
-// FUSED = false: x is given (plain staging).  FUSED = true: the x-producer prologue of xprod.cuh (separate instantiation so
-// that the plain kernel's instruction footprint stays small).
-template <int KVA, int KVB, int S, bool FUSED>
+// XMODE = 0: x is given (plain staging).  1: the x-producer prologue of xprod.cuh (separate instantiation so that the plain
+// kernel's instruction footprint stays small).  2: ... with one operand polled out of the row-sharded LL receive buffer.
+template <int KVA, int KVB, int S, int XMODE>
 __global__ void __launch_bounds__(kTcqThreads, kGemvCtasPerSM)
 tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit splitB, float *__restrict__ out,
                 const uint32_t *__restrict__ x32, const uint32_t *__restrict__ tlut, int M, int K, int bs, XProd prod) {
@@ -178,7 +178,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     TcqTableRegs<S> tregs;
     tcq_table_load<S>(tregs, tlut);
     QP_PHASE(1);
-    if constexpr (FUSED) {
+    if constexpr (XMODE != 0) {
         float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
         // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
         auto finish_prologue = [&](auto ch_tag) {
@@ -190,7 +190,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
             QP_PHASE(2);
             pdl_wait();  // x (and out) are produced by the preceding kernel
             QP_PHASE(3);
-            produce_x<CH>(xs, xscratch, red, prod, K, pre);
+            produce_x<CH, XMODE == 2>(xs, xscratch, red, prod, K, pre);
         };
         if (((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
         else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
@@ -327,12 +327,13 @@ template <int KVA, int KVB, int S>
 static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void *tlut, int M, int K, int bs,
                        const XProd &prod, cudaStream_t st) {
     const bool fused = prod.mode != 0;
-    auto kern = fused ? tcq_gemv_kernel<KVA, KVB, S, true> : tcq_gemv_kernel<KVA, KVB, S, false>;
+    auto kern = prod.mode == 0 ? tcq_gemv_kernel<KVA, KVB, S, 0>
+                               : (prod.mode == 1 ? tcq_gemv_kernel<KVA, KVB, S, 1> : tcq_gemv_kernel<KVA, KVB, S, 2>);
     const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the shared-memory budget of the %s GEMV", K,
                  fused ? "fused-prologue" : "plain");
-    static DeviceOnce configured[2];
-    if (configured[fused].first()) {
+    static DeviceOnce configured[3];
+    if (configured[prod.mode].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
     }
     const int nctas = sm_count() * kGemvCtasPerSM;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void xphase_stamp(int i) {
 #endif
 
 struct XProd {
-    int mode;                 // 0: x is given (plain staging); 1: produce x as described above
+    int mode;                 // 0: x is given (plain staging); 1: produce x as described above; 2: ... with the LL operand
     const __half *src;        // h (n)
     __half *h_out;            // h' destination or NULL
     const float *acc;         // optional fp32 accumulators (n) of the previous projection
@@ -43,7 +43,30 @@ struct XProd {
     float *zero2;
     int zero2_count;
     int m, Kf;                // Hadamard block / 28-factor of n
+    // row-sharded mode: the gathered operand arrives from the peers as "LL" words {2 x fp16, epoch, 2 x fp16, epoch} in a
+    // local receive buffer (xchg_send_ll_kernel of every rank stores there over NVLink) and is polled here, in every CTA
+    const uint4 *ll;          // n / 4 entries, or NULL
+    const unsigned *ll_epoch; // epoch the entries must carry (written by the local sender launched in front of this kernel)
+    int ll_kind;              // 1: the LL values are fp16(acc) (src is read normally); 2: they are src
+    unsigned long long ll_spin_cycles;  // 0 = poll forever
 };
+
+// LL entries are read at L2 (ld.volatile), where the peers' NVLink stores land; an 8-byte {data, flag} half of an entry is
+// written by one store, so a matching flag implies its data.  xp_ll_load issues the read; xp_ll_wait re-reads until both flags
+// carry `ep` (normally zero times: the sender kernel of this rank has already completed, the peers' are a few us apart).
+__device__ __forceinline__ uint4 xp_ll_load(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 xp_ll_wait(uint4 v, const uint4 *p, unsigned ep, unsigned long long limit) {
+    const long long t0 = clock64();
+    while (v.y != ep || v.w != ep) {
+        if (limit != 0ull && (unsigned long long)(clock64() - t0) > limit) __trap();  // a peer died: fail, do not hang the GPU
+        v = xp_ll_load(p);
+    }
+    return make_uint2(v.x, v.z);
+}
 
 __device__ __forceinline__ float xp_block_sum(float v, float *red) {
 #pragma unroll
@@ -111,7 +134,7 @@ __device__ __forceinline__ void xp_preload(XPre<CH> &r, const XProd &p, int n) {
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
         const bool ok = c < nch;
-        r.wv[j] = (ok && p.acc) ? __ldg(reinterpret_cast<const uint2 *>(p.wscale) + c) : make_uint2(0u, 0u);
+        r.wv[j] = (ok && (p.acc || p.ll_kind == 1)) ? __ldg(reinterpret_cast<const uint2 *>(p.wscale) + c) : make_uint2(0u, 0u);
         r.nv[j] = (ok && p.norm_w) ? __ldg(reinterpret_cast<const uint2 *>(p.norm_w) + c) : make_uint2(0u, 0u);
         r.sv[j] = (ok && p.su) ? __ldg(reinterpret_cast<const uint2 *>(p.su) + c) : make_uint2(0u, 0u);
     }
@@ -119,17 +142,42 @@ __device__ __forceinline__ void xp_preload(XPre<CH> &r, const XProd &p, int n) {
 
 // produce x (n = K values) into xs in the B-fragment order stage_x() uses (bs = 1).  v: n floats of shared scratch.
 // CH = ceil(n / 4 / blockDim.x) chunks of 4 consecutive elements per thread.
-template <int CH>
+// LL (compile time): one operand is polled out of the row-sharded receive buffer (p.ll); a separate instantiation because the
+// polling registers and branches cost the single-GPU prologue 1.3 % of a decode step when they are merely present (measured)
+template <int CH, bool LL = false>
 __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n, const XPre<CH> &pre) {
     const int nch = n >> 2, T = blockDim.x;
     QP_XPHASE(0);
     uint2 hv[CH];
     float4 av[CH];
     const uint2 (&wv)[CH] = pre.wv, (&nv)[CH] = pre.nv, (&sv)[CH] = pre.sv;
+    const uint4 *const p_ll = LL ? p.ll : nullptr;
+    const unsigned ll_ep = p_ll ? __ldcg(p.ll_epoch) : 0u;
+    uint4 lv[CH];
+    if (p_ll) {  // row-sharded: one of the two operands comes out of the LL receive buffer; all reads in flight before the first check
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int c = threadIdx.x + j * T;
+            lv[j] = c < nch ? xp_ll_load(p_ll + c) : make_uint4(0u, ll_ep, 0u, ll_ep);
+            if (p.ll_kind != 2) hv[j] = c < nch ? __ldcg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
         const bool ok = c < nch;
+        if (p_ll) {
+            const uint2 g = xp_ll_wait(lv[j], p_ll + (ok ? c : 0), ll_ep, p.ll_spin_cycles);
+            if (p.ll_kind == 2) {
+                hv[j] = g;
+                av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float a4[4];
+                xp_unpack4(g, a4);  // fp16(acc): exactly what the arithmetic below makes of an fp32 accumulator first
+                av[j] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+            }
+            continue;
+        }
         // activations / accumulators are rewritten by other kernels within one decode step and kernels overlap under programmatic
         // dependent launch: read them at L2 (ld.global.cg), never through the non-coherent L1 path (measured round 2: with
         // ld.global.nc a CTA could see a stale line of `acc` / `src` and the fused launch list diverged from the un-fused one)
@@ -144,7 +192,7 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
         xp_unpack4(hv[j], y[j]);
-        if (p.acc) {
+        if (p.acc || p.ll_kind == 1) {
             float w4[4];
             xp_unpack4(wv[j], w4);
             const float a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
@@ -217,16 +265,17 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
 
 // dispatch on the chunk count (n <= 15360 for 768 threads; larger n does not fit the shared-memory budget anyway);
 // this form loads everything after the caller's dependency wait
+template <bool LL = false>
 __device__ __forceinline__ void produce_x_dispatch(uint32_t *xs, float *v, float *red, const XProd &p, int n) {
     const int ch = ((n >> 2) + blockDim.x - 1) / blockDim.x;
     if (ch <= 2) {
         XPre<2> pre;
         xp_preload<2>(pre, p, n);
-        produce_x<2>(xs, v, red, p, n, pre);
+        produce_x<2, LL>(xs, v, red, p, n, pre);
     } else {  // host guarantees n <= 5 * 4 * blockDim.x
         XPre<5> pre;
         xp_preload<5>(pre, p, n);
-        produce_x<5>(xs, v, red, p, n, pre);
+        produce_x<5, LL>(xs, v, red, p, n, pre);
     }
 }
 

@@ -37,7 +37,7 @@ SIGNATURES = {
     "qp_scale_epilogue": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "qp_fused_norm_had": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp],
     "qp_fused_norm_had_xchg": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _vp, _i, _f, _i, _vp, _i, _vp, _vp],
-    "qp_xchg_gather": [_vp, _i, _vp, _vp],
+    "qp_xchg_send_ll": [_vp, _i, _i, _vp, _i, _vp, _vp],
     "qp_silu_mul_had_grid_xchg": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp, _vp],
     "qp_set_spin_timeout_ms": [ctypes.c_longlong],
     "qp_peer_alloc": [_vp, ctypes.c_size_t],
@@ -64,7 +64,8 @@ class XProd(ctypes.Structure):
     """mirror of `qp_xprod` (include/qpalette.h)"""
     _fields_ = [("src_f16", _vp), ("h_out_f16", _vp), ("acc", _vp), ("wscale_f16", _vp), ("acc_scale", _f),
                 ("norm_w_f16", _vp), ("eps", _f), ("su_f16", _vp), ("had_scale", _f), ("x_out_f16", _vp),
-                ("zero1", _vp), ("zero1_count", _i), ("zero2", _vp), ("zero2_count", _i)]
+                ("zero1", _vp), ("zero1_count", _i), ("zero2", _vp), ("zero2_count", _i),
+                ("ll", _vp), ("ll_epoch", _vp), ("ll_kind", _i)]
 
 
 class Xchg(ctypes.Structure):

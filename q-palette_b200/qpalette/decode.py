@@ -242,7 +242,9 @@ class DecodeRunner:
             # the four gathered buffers live in a region every peer maps; site = 4 * layer + {attn, o, act, down}
             from .peer import PeerRegion
             try:
-                self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4), ("z", I * 4)],
+                # ll_*: receive buffers of the low-latency gather in front of the fused GEMV prologues (4 bytes per element)
+                self.region = PeerRegion([("attn", H * 2), ("acc_o", H * 4), ("act", I * 2), ("acc_dn", H * 4), ("z", I * 4),
+                                          ("ll_attn", H * 4), ("ll_acc_o", H * 4), ("ll_acc_dn", H * 4)],
                                          4 * self.L + 4, rank, world, process_group, self.dev)
             except Exception as ex:  # e.g. CUDA IPC not permitted between these processes
                 self.region = None
@@ -296,9 +298,10 @@ class DecodeRunner:
         return self._step_unfused()
 
     def _step_fused_tp(self):
-        """row-sharded decode step with the glue fused into the GEMV prologues: per layer 3 exchange kernels (complete the
-        gathered buffer in place over NVLink peer memory, qp_xchg_gather) + 4 GEMVs (3 of them computing residual / RMSNorm /
-        sign / Hadamard of the completed buffer in all of their CTAs) + attention + the exchanging SiLU*mul/Hadamard kernel.
+        """row-sharded decode step with the glue fused into the GEMV prologues: per layer 3 fire-and-forget senders (this rank's
+        slice as fp16 + epoch "LL" entries into every rank's receive buffer over NVLink peer memory, qp_xchg_send_ll) + 4 GEMVs
+        (3 of them polling the receive buffer and computing residual / RMSNorm / sign / Hadamard of the gathered vector in all of
+        their CTAs) + attention + the exchanging SiLU*mul/Hadamard kernel.
         Replaces the three single-CTA 8192-point norm/Hadamard kernels of the un-fused sharded list (~7 us each).
         Exchange sites and accumulator-clearing duties are those of _step_unfused (clear-before-flag protocol)."""
         L, st = lib(), torch.cuda.current_stream().cuda_stream
@@ -311,13 +314,21 @@ class DecodeRunner:
         hc, ho = self.h, self.h2
         check(L.qp_embed(p(hc), p(self.embed), p(self.token), H, st))
 
-        def gather(name, site, zero):
-            xc = self.region.xchg(name, site)
-            keep.append(xc)
-            check(L.qp_xchg_gather(p(zero), zero.numel() if zero is not None else 0, ctypes.byref(xc), st))
+        ll_site = {"attn": 4 * self.L, "acc_o": 4 * self.L + 1, "acc_dn": 4 * self.L + 2}
 
-        def xp(src, h_out=None, acc=None, ws=None, norm=None, su=None, scale=s_h):
-            return _cabi.XProd(p(src), p(h_out), p(acc), p(ws), S, p(norm), sh.rms_norm_eps, p(su), scale, None, None, 0, None, 0)
+        def send(name, src_slice, is_f32, zero):
+            """publish this rank's H / world elements of a gathered vector into every rank's LL receive buffer; returns the
+            (buffer, epoch word) pair the consumer's prologue polls.  One epoch counter per BUFFER (not per layer): every use of
+            the buffer must carry a value its previous contents cannot have."""
+            site = ll_site[name]
+            xc = self.region.xchg("ll_" + name, site)
+            keep.append(xc)
+            check(L.qp_xchg_send_ll(src_slice, is_f32, Ho, p(zero), zero.numel() if zero is not None else 0, ctypes.byref(xc), st))
+            return self.region.base + self.region.offsets["ll_" + name][0], self.region.epoch.data_ptr() + 4 * site
+
+        def xp(src, h_out=None, acc=None, ws=None, norm=None, su=None, scale=s_h, ll=None, ll_kind=0):
+            return _cabi.XProd(p(src), p(h_out), p(acc), p(ws), S, p(norm), sh.rms_norm_eps, p(su), scale, None, None, 0, None, 0,
+                               ll[0] if ll else None, ll[1] if ll else None, ll_kind)
 
         def run_group(projs, acc_buf, acc_off, prod):
             lead = next(i for i, (pr, _) in enumerate(projs) if pr.can_fuse())
@@ -333,18 +344,18 @@ class DecodeRunner:
             if prev is None:
                 prod = xp(hc, norm=ly["norm1"], su=ly["SU_qkv"])  # acc_qkv was cleared by the previous step's last exchange
             else:
-                gather("acc_dn", 4 * (li - 1) + 3, self.acc_qkv)
-                prod = xp(hc, h_out=ho, acc=self.acc_dn, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"])
+                ll = send("acc_dn", p(self.acc_dn) + 4 * rank * Ho, 1, self.acc_qkv)
+                prod = xp(hc, h_out=ho, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"], ll=ll, ll_kind=1)
             run_group(ly["qkv"], self.acc_qkv, 0, prod)
             if prev is not None:
                 hc, ho = ho, hc
             check(L.qp_rope_attention(p(self.attn) + 2 * rank * (H // world), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq),
                                       p(ly["kc"]), p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
                                       sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
-            gather("attn", 4 * li + 0, self.acc_o)
-            run_group([(ly["o"], 0)], self.acc_o, rank * Ho, xp(self.attn, su=ly["SU_o"]))
-            gather("acc_o", 4 * li + 1, self.acc_ug)
-            run_group(ly["ug"], self.acc_ug, 0, xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"]))
+            ll = send("attn", p(self.attn) + 2 * rank * Ho, 0, self.acc_o)
+            run_group([(ly["o"], 0)], self.acc_o, rank * Ho, xp(self.attn, su=ly["SU_o"], ll=ll, ll_kind=2))
+            ll = send("acc_o", p(self.acc_o) + 4 * rank * Ho, 1, self.acc_ug)
+            run_group(ly["ug"], self.acc_ug, 0, xp(hc, h_out=ho, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"], ll=ll, ll_kind=1))
             hc, ho = ho, hc
             xc = self.region.xchg("z", 4 * li + 2)
             keep.append(xc)

@@ -164,3 +164,71 @@ def test_silu_mul_had_grid_self_exchange(I):
             assert torch.equal(xs[0], xs[1])
     finally:
         reg.close()
+
+
+@pytest.mark.parametrize("kind", ["acc", "src"])
+@pytest.mark.parametrize("K", [4096, 8192])
+def test_ll_gather_into_fused_gemv(kind, K):
+    """qp_xchg_send_ll + the LL polling of the fused GEMV prologue (qp_xprod.ll): each "rank" publishes its half of the gathered
+    vector (fp32 accumulators -> fp16, or the fp16 attention output) into both receive buffers, then runs the consumer GEMV on
+    its own receive buffer.  Must equal the same GEMV fed with the complete vector: residual stream bit for bit, x bit for bit,
+    outputs within the atomics noise.  (Senders first, then consumers: on ONE device a 148-CTA consumer would starve the other
+    rank's sender of an SM; two processes on two GPUs have no such coupling.)"""
+    from qpalette import _cabi
+    from qpalette._cabi import SPLIT_IN, check, lib
+    L = lib()
+    M, S, eps, scale = 512, 9, 1e-5, 64.0
+    rng = np.random.default_rng(K + (kind == "src"))
+    had_scale = 1.0 / (math.sqrt(K) * scale)
+    b1 = torch.from_numpy(rng.integers(0, 256, size=M * (K // 2) * 6 // 16, dtype=np.uint8)).cuda()
+    b2 = torch.from_numpy(rng.integers(0, 256, size=M * (K // 2) * 7 // 16, dtype=np.uint8)).cuda()
+    tl = torch.from_numpy((rng.standard_normal((1 << S, 2)) * 0.9).astype(np.float16)).cuda()
+    ws = torch.from_numpy((rng.uniform(0.5, 1.5, K) / 64 / 40).astype(np.float16)).cuda()
+    nw = torch.from_numpy(rng.uniform(0.5, 1.5, K).astype(np.float16)).cuda()
+    su = torch.from_numpy(rng.choice([-1.0, 1.0], K).astype(np.float16)).cuda()
+    reg = TwoRegions(K * 4, nsites=2)
+    p = lambda t: t.data_ptr() if t is not None else None
+    st = torch.cuda.current_stream().cuda_stream
+
+    def consumer(src, acc, ll, ll_epoch, ll_kind):
+        h_out = torch.zeros(K, dtype=torch.float16, device="cuda")
+        x_out = torch.zeros(K, dtype=torch.float16, device="cuda")
+        out = torch.zeros(M, dtype=torch.float32, device="cuda")
+        if kind == "acc":
+            xp = _cabi.XProd(p(src), p(h_out), p(acc), p(ws), scale, p(nw), eps, p(su), had_scale, p(x_out), None, 0, None, 0,
+                             ll, ll_epoch, ll_kind)
+        else:
+            xp = _cabi.XProd(p(src), None, None, None, scale, None, eps, p(su), had_scale, p(x_out), None, 0, None, 0,
+                             ll, ll_epoch, ll_kind)
+        check(L.qp_tcq_gemv_fused(p(out), p(b1), p(b2), ctypes.addressof(xp), p(tl), M, K, S, 6, 7, SPLIT_IN, K // 2, st))
+        torch.cuda.synchronize()
+        return h_out, x_out, out
+
+    try:
+        for epoch in range(3):
+            h = torch.from_numpy(rng.standard_normal(K).astype(np.float16)).cuda()
+            acc = torch.from_numpy((rng.standard_normal(K) * 40).astype(np.float32)).cuda()
+            zero = [torch.ones(555, dtype=torch.float32, device="cuda") for _ in range(2)]
+            keep = []
+            for r in range(2):
+                xc = reg.xchg(r, 1, K * 4 // 2)
+                keep.append(xc)
+                sl = slice(r * K // 2, (r + 1) * K // 2)
+                src = acc[sl].contiguous() if kind == "acc" else h[sl].contiguous()
+                keep.append(src)
+                check(L.qp_xchg_send_ll(p(src), 1 if kind == "acc" else 0, K // 2, p(zero[r]), 555, ctypes.byref(xc), st))
+            torch.cuda.synchronize()
+            want = consumer(h, acc if kind == "acc" else None, None, None, 0)
+            for r in range(2):
+                assert float(zero[r].abs().sum()) == 0.0
+                assert int(reg.epochs[r][1]) == epoch + 1
+                # a consumer that does not own the complete vector: poison what the LL entries replace
+                src = h if kind == "acc" else torch.full_like(h, float("nan"))
+                got = consumer(src, None, reg.bases[r], reg.epochs[r].data_ptr() + 4, 1 if kind == "acc" else 2)
+                if kind == "acc":
+                    assert torch.equal(got[0], want[0])                                   # h' = h + fp16(acc) * Wscale * s
+                assert torch.equal(got[1], want[1])                                       # x
+                a, b = got[2].double(), want[2].double()
+                assert float((a - b).norm() / b.norm()) <= 1e-3
+    finally:
+        reg.close()

@@ -77,14 +77,14 @@ sqd, smi = uniform_qdict(small, "tcomb_6_7_0.5_none_0.9"), [["merge_qkv", "merge
 single = DecodeRunner(small, sqd, smi, max_seq=64, seed=5, fused=False)   # same seed -> same full-width weights: the oracle side
 caches = [([], []) for _ in single.layers]
 tok, refs = 3, []
+for step in range(3):  # the oracle side follows its OWN greedy tokens, independently of any GPU run
+    refs.append(R.decode_step_ref(single, single.embed[tok].cpu().numpy(), step, caches)[1])
+    tok = int(np.argmax(refs[step]))
 for mode in ("p2p", "p2p_unfused", "nccl"):
     r = DecodeRunner(small, sqd, smi, max_seq=64, seed=5, rank=rank, world=world, process_group=dist.group.WORLD,
                      p2p=mode.startswith("p2p"), fused=(mode == "p2p"))
     r.reset(3)
-    tok = 3
     for step in range(3):
-        if mode == "p2p":
-            refs.append(R.decode_step_ref(single, single.embed[tok].cpu().numpy(), step, caches)[1])
         r.step()
         torch.cuda.synchronize()
         lg = r.logits.float().cpu().numpy().astype(np.float64)
@@ -93,7 +93,6 @@ for mode in ("p2p", "p2p_unfused", "nccl"):
         ok &= good
         print(f"[rank {rank}] small {mode:11s} step {step}: rel-L2 of logits vs oracle restatement {err:.2e} "
               f"{'OK' if good else 'MISMATCH'}", flush=True)
-        tok = int(r.token.item())
 dist.barrier(); torch.cuda.synchronize()
 print(f"[rank {rank}] {'ALL OK' if ok else 'FAILED'}", flush=True)
 sys.stdout.flush()
