@@ -13,6 +13,8 @@ Metric (BASELINE.json): bs=1 decode tokens/s of Llama-3.1-8B with every linear q
             sampled token comes back device -> pinned host and the host waits for it
   roofline  the dominant kernel (fused trellis-decode GEMV, 4096x14336 tcomb_6_7) timed alone with CUDA events over the
             model's 32 distinct down_proj buffers (764 MB > L2), algorithmic bytes / time vs the measured HBM peak
+  extra     long_context: the same model decoding at positions 2051..2082 (N = 1); tp70b: the 70B-shaped model with the rows of
+            every layer sharded over the N GPUs (every N; N = 1 is the un-sharded number the efficiency is taken against)
   cpu_baseline / --impl reference: the reference's dequantize->matvec path restated in C (oracle/qp_cref.c, all host
             threads) on a bounded sample, extrapolated to tokens/s
 N > 1 (default `--parallel replicas`): N independent bs=1 decode streams, one per GPU, no data-path collective (decode
@@ -288,7 +290,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (invalid as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tp-extra", action="store_true",
-                    help="skip the additional row-sharded 70B-shaped measurement printed under extra.tp70b")
+                    help="skip the additional measurements printed under extra (long_context, tp70b)")
     ap.add_argument("--unfused", action="store_true",
                     help="debug: separate RMSNorm/Hadamard launches instead of the fused GEMV prologues (9 launches per layer)")
     args = ap.parse_args()
@@ -382,7 +384,7 @@ def main():
 
     # ---- roofline of the dominant kernel (rank 0) -------------------------------------------------------------------
     roofline, detail = None, {}
-    if rank == 0 and args.workload == "8b" and tp == 1:
+    if rank == 0 and args.workload in ("8b", "figure1d", "figure1c") and tp == 1:
         peak, peak_kind = measured_peak()
 
         def time_proj(projs, x, out, iters=5):
@@ -403,30 +405,49 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) * 1e-3 / (iters * len(projs))
 
-        downs = [ly["down"] for ly in runner.layers]                 # 4096 x 14336, 32 distinct buffers = 764 MB > L2
-        ugs = [ly["ug"][0][0] for ly in runner.layers]               # 28672 x 4096
-        qkvs = [ly["qkv"][0][0] for ly in runner.layers]             # 6144 x 4096
-        os_ = [ly["o"] for ly in runner.layers]                      # 4096 x 4096
         alg = lambda p: p.weight_bytes + 2 * p.K + 4 * p.M + 2048    # codes + x (fp16) + out (fp32) + tlut
-        t_down = time_proj(downs, runner.x_i, runner.acc_dn)
+        xbuf = {runner.H: runner.x_h, runner.I: runner.x_i}
+        scratch_out = torch.zeros(2 * runner.I, dtype=torch.float32, device="cuda")
+        if args.workload == "8b":
+            downs = [ly["down"] for ly in runner.layers]                 # 4096 x 14336, 32 distinct buffers = 764 MB > L2
+            ugs = [ly["ug"][0][0] for ly in runner.layers]               # 28672 x 4096
+            qkvs = [ly["qkv"][0][0] for ly in runner.layers]             # 6144 x 4096
+            os_ = [ly["o"] for ly in runner.layers]                      # 4096 x 4096
+            dom, dom_name = downs, "tcq_gemv_kernel<6,7,9> 4096x14336 (down_proj)"
+            others = (("ug_28672x4096", ugs), ("qkv_6144x4096", qkvs), ("o_4096x4096", os_))
+        else:
+            # mixed-scheme model: the dominant kernel is the (quantizer, layout, shape) group that streams the most bytes per token
+            groups = {}
+            for ly in runner.layers:
+                for pr in [ly["down"], ly["o"]] + [m for m, _ in ly["ug"]] + [m for m, _ in ly["qkv"]]:
+                    groups.setdefault((pr.qs, bool(getattr(pr, "simt", False)), pr.M, pr.K), []).append(pr)
+            ranked = sorted(groups.items(), key=lambda kv: -sum(p.weight_bytes for p in kv[1]))
+            (qs, simt, M_, K_), dom = ranked[0]
+            dom_name = f"{qs}{' (SIMT layout)' if simt else ''} {M_}x{K_}, {len(dom)} launches per token"
+            others = tuple((f"{q}{'_simt' if s_ else ''}_{m}x{k}", ps) for (q, s_, m, k), ps in ranked[1:4])
+        t_dom = time_proj(dom, xbuf[dom[0].K], scratch_out)
         # DRAM traffic per launch cannot be measured without ncu: it is quoted from the committed capture (and says so)
         traffic, traffic_source = None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
-            ent = prof.get("tcq_gemv_4096x14336_tcomb_6_7", {})
-            traffic, traffic_source = ent.get("dram_bytes_per_launch"), "not measured in this run: " + ent.get("source", "profiles/summary.json")
-        except Exception:
-            pass
-        ach = alg(downs[0]) / t_down / 1e9
-        roofline = {"bound": "hbm", "kernel": "tcq_gemv_kernel<6,7,9> 4096x14336 (down_proj)", "achieved": ach, "peak": peak,
+        if args.workload == "8b":
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
+                ent = prof.get("tcq_gemv_4096x14336_tcomb_6_7", {})
+                traffic, traffic_source = ent.get("dram_bytes_per_launch"), "not measured in this run: " + ent.get("source", "profiles/summary.json")
+            except Exception:
+                pass
+        ach = alg(dom[0]) / t_dom / 1e9
+        rotated = sum(p.weight_bytes for p in dom)
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak,
                     "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_source,
-                    "algorithmic_bytes": alg(downs[0]), "us_per_launch": t_down * 1e6}
-        for name, projs, x, out in (("ug_28672x4096", ugs, runner.x_h, runner.acc_ug), ("qkv_6144x4096", qkvs, runner.x_h, runner.acc_qkv),
-                                    ("o_4096x4096", os_, runner.x_h, runner.acc_o)):
-            t = time_proj(projs, x, out)
+                    "algorithmic_bytes": alg(dom[0]), "us_per_launch": t_dom * 1e6,
+                    "rotation": f"{len(dom)} distinct weight buffers, {rotated / 1e6:.0f} MB"
+                                f"{'' if rotated > 252e6 else ' (< 2 x L2: partly L2-resident, an upper bound)'}"}
+        for name, projs in others:
+            t = time_proj(projs, xbuf[projs[0].K], scratch_out)
             detail[name] = {"us_per_launch": t * 1e6, "GBps": alg(projs[0]) / t / 1e9}
         detail["token_bytes"] = runner.bytes_per_token()
         detail["token_GBps"] = runner.bytes_per_token() * tok_s / 1e9
+        del scratch_out
 
     # ---- CPU baseline beside it (rank 0, N = 1) ---------------------------------------------------------------------
     cpu = None
@@ -441,11 +462,37 @@ def main():
         except Exception as ex:  # the checker library is test infrastructure; a missing one must not hide the GPU number
             cpu = {"value": None, "unit": "tok/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
 
-    # ---- row-sharded 70B-shaped decode (BASELINE configs[4]) measured in the same run: every rank takes part --------------
     runner_L, bytes_per_token = runner.L, runner.bytes_per_token()
     extra = {}
+    # ---- one long-context point (the timed region above sits at positions < max_seq = 152, the reference's --max_new_tokens 64
+    # regime): the same model decoding at position 2048, where rope_attention_kernel (one 256-thread CTA per head) reads 2 K rows
+    if rank == 0 and world == 1 and args.workload == "8b" and args.layers is None and not args.no_tp_extra:
+        try:
+            del runner
+            torch.cuda.empty_cache()
+            lc = DecodeRunner(shape, qdict, merge_info, max_seq=2048 + 64, seed=0, fused=not args.unfused)
+            lc.capture()
+            lc.reset(1, pos=2048)
+            for _ in range(3):
+                lc.step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(32):
+                lc.step()
+            b.record(stream)
+            torch.cuda.synchronize()
+            lc_ms = a.elapsed_time(b) / 32
+            extra["long_context"] = {"positions": "2051..2082", "tok_s": 1e3 / lc_ms, "ms_per_step": lc_ms,
+                                     "note": "KV rows below 2048 are zero-filled (timing only)"}
+            del lc
+        except Exception as ex:
+            extra["long_context"] = {"error": f"{type(ex).__name__}: {ex}"}
+        runner = None
+        torch.cuda.empty_cache()
+    # ---- row-sharded 70B-shaped decode (BASELINE configs[4]) measured in the same run: every rank takes part --------------
     if args.workload == "8b" and args.parallel == "replicas" and not args.no_tp_extra and args.layers is None:
-        del runner
+        runner = None
         torch.cuda.empty_cache()
         try:
             extra["tp70b"] = measure_tp70b(world, rank, pg, min(args.steps, 20), 3)

@@ -189,11 +189,15 @@ int qp_silu_mul_had_grid(void *x_out_f16, float *acc, const void *wscale_f16, fl
                          float had_scale, float *zero_ptr, int zero_count, unsigned *sync_counter, void *stream);
 /* acc_qkv = [q | k | v] fp32 GEMV sums ([q | v | k] when qvk_order != 0: a merge_qv layer, whose Wscale_qkv the reference
  * stores in that order, lib/linear/incoherent_linear.py:211-213): Wscale epilogue, RoPE, KV-cache append at *pos_ptr, causal
- * attention of the new token over the cache; one CTA per query head (IncoherentSdpaAttention.forward, :110-203).
+ * attention of the new token over the cache (IncoherentSdpaAttention.forward, :110-203).  D = 128: grid (heads, ceil(max_seq /
+ * 128)), each CTA takes 128 positions of one query head and the last one to finish combines the partial softmaxes; `scratch`
+ * (qp_rope_attention_scratch_bytes(H, D, max_seq) bytes, zeroed ONCE by the caller; may be NULL when that is 0) holds the
+ * partials and one ticket per head, and may be shared by all layers of a stream.  Other head sizes: one CTA per head.
  * *pos_ptr >= max_seq is clamped to the last cache row (memory safety only; the host API refuses to step that far). */
+size_t qp_rope_attention_scratch_bytes(int H, int D, int max_seq);
 int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,
                       const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H, int Hkv,
-                      int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *stream);
+                      int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *scratch, void *stream);
 /* fp16 GEMV for the unquantized lm_head: out (rows) fp32 = W (rows, K) @ x (K) */
 int qp_gemv_f16(float *out, const void *W_f16, const void *x_f16, int rows, int K, void *stream);
 int qp_argmax(int *token_out, const float *logits, int n, void *scratch, void *stream);

@@ -648,37 +648,178 @@ silu_mul_had_grid_xchg_kernel(__half *__restrict__ x_out, const float *__restric
     }
 }
 
-// One CTA (256 threads) per query head.  acc_qkv: fp32 [q (H*D) | k (Hkv*D) | v (Hkv*D)] raw GEMV sums; wscale same layout.
+// Attention of one new token.  acc_qkv: fp32 [q (H*D) | k (Hkv*D) | v (Hkv*D)] raw GEMV sums; wscale same layout.
 // RoPE (HF rotate_half convention, model/llama.py apply_rotary_pos_emb) with inv_freq table (D/2 floats, llama3 scaling
 // already applied by the host).  KV cache: fp16 [max_seq][Hkv][D] per layer.  pos read from device memory.
-// D = 128: a warp covers one cached position with one 8-byte load per lane; 8 positions are in flight per warp.
+// D = 128 (rope_attention_split_kernel): grid (heads, splits); a CTA takes kAttnChunk = 128 positions of one query head, a
+// warp covers a cached position with one 8-byte load per lane and has ALL of its 16 K rows and 16 V rows in flight at once,
+// issued before the dependency wait: a split costs one memory round trip whatever the context length.  Splits beyond the
+// current position exit at once; with one active split (pos < 128) the result is written directly, otherwise the splits leave
+// (max, sum, unnormalised output) partials and the last one to finish (a ticket per head) combines them.  Measured at
+// position 2048: 4.45 ms / token with the single-CTA loop of round 1 (33 dependent round trips per layer) -- see DESIGN.md.
+// Other head sizes: rope_attention_kernel, one CTA per head looping over the context.
 constexpr int kAttnThreads = 256;
+constexpr int kAttnChunk = 128;                                  // positions per split
+constexpr int kAttnRows = kAttnChunk / (kAttnThreads / 32);      // cached rows per warp and split
+constexpr int kAttnPart = 128 + 4;                               // floats per partial: o[128], max, sum, pad
+
+__global__ void __launch_bounds__(kAttnThreads)
+rope_attention_split_kernel(__half *__restrict__ attn_out, const float *__restrict__ acc_qkv, const __half *__restrict__ wscale,
+                            float acc_scale, const float *__restrict__ inv_freq, __half *__restrict__ kcache,
+                            __half *__restrict__ vcache, const int *__restrict__ pos_ptr, int H, int Hkv, int max_seq,
+                            int qvk_order, float *__restrict__ zero_ptr, int zero_count, float *__restrict__ part_buf,
+                            unsigned *__restrict__ tickets, int S) {
+    constexpr int D = 128, C = kAttnChunk, nw = kAttnThreads / 32;
+    __shared__ __align__(16) float q[D], kn[D], vn[D], part[nw][D], sc[C + 4];
+    __shared__ float red[32];
+    __shared__ unsigned s_ticket;
+    const int head = blockIdx.x, split = blockIdx.y, kvh = head / (H / Hkv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a position past the cache capacity would write out of bounds: clamp (DecodeRunner.step refuses to go that far)
+    const int pos = min(__ldcg(pos_ptr), max_seq - 1);
+    const int nact = pos / C + 1;  // splits that hold a position <= pos
+    if (split >= nact) return;
+    const bool owner = split == nact - 1;                 // holds position pos itself (taken from shared memory, not the cache)
+    const int t_lo = split * C, t_hi = min(pos, t_lo + C);  // cached rows [t_lo, t_hi) of this split
+    // cached rows were written by earlier decode steps, not by the preceding kernel: fetched before the dependency wait
+    uint2 kpre[kAttnRows], vpre[kAttnRows];
+#pragma unroll
+    for (int u = 0; u < kAttnRows; ++u) {
+        const int t = t_lo + warp + u * nw;
+        const size_t row = ((size_t)t * Hkv + kvh) * D;
+        kpre[u] = (t < t_hi) ? __ldcg(reinterpret_cast<const uint2 *>(kcache + row) + lane) : make_uint2(0u, 0u);
+        vpre[u] = (t < t_hi) ? __ldcg(reinterpret_cast<const uint2 *>(vcache + row) + lane) : make_uint2(0u, 0u);
+    }
+    // likewise independent of the preceding kernel: the per-row scales and the rotary angle of this position
+    const int d = threadIdx.x;
+    constexpr int half = D / 2;
+    const int pd = d < half ? d + half : d - half;
+    // accumulator / Wscale order: q | k | v, or q | v | k for a merge_qv layer (lib/linear/incoherent_linear.py:211-213)
+    const int iq = head * D, ik = (qvk_order ? H + Hkv : H) * D + kvh * D, iv = (qvk_order ? H : H + Hkv) * D + kvh * D;
+    float wq = 0.f, wqp = 0.f, wk = 0.f, wkp = 0.f, wv = 0.f, c16 = 0.f, s16 = 0.f;
+    if (d < D) {
+        wq = __half2float(wscale[iq + d]), wqp = __half2float(wscale[iq + pd]), wk = __half2float(wscale[ik + d]);
+        wkp = __half2float(wscale[ik + pd]), wv = __half2float(wscale[iv + d]);
+        const float fr = inv_freq[d % half];
+        double snd, csd;  // precise range reduction (the build uses --use_fast_math)
+        sincos((double)pos * (double)fr, &snd, &csd);
+        // fp16 rounding of cos/sin as the fp16 reference graph does
+        c16 = __half2float(__float2half((float)csd)), s16 = __half2float(__float2half((float)snd));
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    if (zero_ptr && blockIdx.x == 0 && split == 0) zero_words4(zero_ptr, zero_count);
+    const __half hs = __float2half(acc_scale);
+    if (d < D) {
+        const float aq = __ldcg(acc_qkv + iq + d), aqp = __ldcg(acc_qkv + iq + pd), ak = __ldcg(acc_qkv + ik + d),
+                    akp = __ldcg(acc_qkv + ik + pd), av = __ldcg(acc_qkv + iv + d);
+        const float sgn = d < half ? -1.f : 1.f;
+        const float qa = scaled_acc(aq, wq, hs), qb = scaled_acc(aqp, wqp, hs);
+        const float ka = scaled_acc(ak, wk, hs), kb = scaled_acc(akp, wkp, hs);
+        q[d] = __half2float(__float2half(qa * c16 + sgn * qb * s16));
+        const __half kr = __float2half(ka * c16 + sgn * kb * s16);
+        const __half vv = __float2half(scaled_acc(av, wv, hs));
+        kn[d] = __half2float(kr);
+        vn[d] = __half2float(vv);
+        if (owner && head % (H / Hkv) == 0) {  // one CTA of the group appends to the cache
+            kcache[((size_t)pos * Hkv + kvh) * D + d] = kr;
+            vcache[((size_t)pos * Hkv + kvh) * D + d] = vv;
+        }
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)D);
+    const float4 q4 = reinterpret_cast<const float4 *>(q)[lane];
+#pragma unroll
+    for (int u = 0; u < kAttnRows; ++u) {
+        const int t = t_lo + warp + u * nw;
+        float k4[4];
+        unpack4(kpre[u], k4);
+        float sdot = q4.x * k4[0] + q4.y * k4[1] + q4.z * k4[2] + q4.w * k4[3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+        if (lane == 0 && t < t_hi) sc[t - t_lo] = sdot * scale;
+    }
+    const int n_loc = t_hi - t_lo + (owner ? 1 : 0);  // scores of this split; the owner's last one is the new token
+    if (owner && warp == 0) {
+        float sdot = 0.f;
+        for (int i = lane; i < D; i += 32) sdot += q[i] * kn[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+        if (lane == 0) sc[n_loc - 1] = sdot * scale;
+    }
+    __syncthreads();
+    float mx = threadIdx.x < n_loc ? sc[threadIdx.x] : -INFINITY;  // n_loc <= C + 1 <= blockDim.x
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    if (threadIdx.x < n_loc) {
+        const float e = __expf(sc[threadIdx.x] - mx);
+        sc[threadIdx.x] = e;
+        sum = e;
+    }
+    sum = block_sum(sum, red);
+    __syncthreads();
+    float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < kAttnRows; ++u) {
+        const int t = t_lo + warp + u * nw;
+        if (t < t_hi) {
+            float v4[4];
+            unpack4(vpre[u], v4);
+            const float w = sc[t - t_lo];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] += w * v4[e];
+        }
+    }
+    reinterpret_cast<float4 *>(part[warp])[lane] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    __syncthreads();
+    float o = 0.f;
+    if (threadIdx.x < D) {
+        o = owner ? sc[n_loc - 1] * vn[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int w = 0; w < nw; ++w) o += part[w][threadIdx.x];
+    }
+    if (nact == 1) {
+        if (threadIdx.x < D) attn_out[head * D + threadIdx.x] = __float2half(o / sum);
+        return;
+    }
+    // several splits: leave the partial, the last split of this head to finish combines
+    float *pb = part_buf + ((size_t)head * S + split) * kAttnPart;
+    if (threadIdx.x < D) pb[threadIdx.x] = o;
+    if (threadIdx.x == 0) pb[D] = mx, pb[D + 1] = sum;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(tickets + head, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(nact - 1)) return;
+    __threadfence();
+    if (threadIdx.x < D) {
+        const float *p0 = part_buf + (size_t)head * S * kAttnPart;
+        float M = -INFINITY;
+        for (int i = 0; i < nact; ++i) M = fmaxf(M, __ldcg(p0 + i * kAttnPart + D));
+        float Lsum = 0.f, O = 0.f;
+        for (int i = 0; i < nact; ++i) {
+            const float w = __expf(__ldcg(p0 + i * kAttnPart + D) - M);
+            Lsum += w * __ldcg(p0 + i * kAttnPart + D + 1);
+            O += w * __ldcg(p0 + i * kAttnPart + threadIdx.x);
+        }
+        attn_out[head * D + threadIdx.x] = __float2half(O / Lsum);
+    }
+    if (threadIdx.x == 0) tickets[head] = 0u;  // ready for the next launch (stream-ordered behind this one)
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ acc_qkv, const __half *__restrict__ wscale,
                       float acc_scale, const float *__restrict__ inv_freq, __half *__restrict__ kcache,
                       __half *__restrict__ vcache, const int *__restrict__ pos_ptr, int H, int Hkv, int D, int max_seq,
                       int qvk_order, float *__restrict__ zero_ptr, int zero_count) {
-    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[8][D] | scores[max_seq]
+    extern __shared__ __align__(16) float sm[];  // q[D] | knew[D] | vnew[D] | part[8][D] | scores[max_seq]   (head sizes other than 128)
     __shared__ float red[32];
     float *q = sm, *kn = sm + D, *vn = sm + 2 * D, *part = sm + 3 * D, *sc = sm + 11 * D;
     const int head = blockIdx.x, kvh = head / (H / Hkv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kAttnThreads / 32;
-    // Cached rows [0, pos) and pos itself were written by earlier decode steps, not by the preceding kernel: the first 64
-    // positions' K and V rows (8 per warp, 8 bytes per lane) are fetched before the dependency wait, so that a short context
-    // costs one memory round trip that overlaps the q/k/v epilogue + RoPE below.
     // a position past the cache capacity would write out of bounds (cache rows and the score array hold max_seq entries):
     // clamp to the last row -- the host API refuses to step that far (DecodeRunner.step), this only keeps memory safe
     const int pos = min(__ldcg(pos_ptr), max_seq - 1);
-    uint2 kpre[8], vpre[8];
-    if (D == 128) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int t = warp + u * nw;
-            const size_t row = ((size_t)t * Hkv + kvh) * D;
-            kpre[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(kcache + row) + lane) : make_uint2(0u, 0u);
-            vpre[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(vcache + row) + lane) : make_uint2(0u, 0u);
-        }
-    }
     // likewise independent of the preceding kernel: the per-row scales and the rotary angle of this position
     const int d = threadIdx.x;
     const int half = D / 2;
@@ -718,37 +859,13 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     __syncthreads();
     const float scale = rsqrtf((float)D);
-    // scores over cached positions [0, pos): lane owns dims 4*lane..+3 (D = 128) -- generic D handled by the strided loop
-    if (D == 128) {
-        const float4 q4 = reinterpret_cast<const float4 *>(q)[lane];
-        for (int t0 = warp; t0 < pos; t0 += nw * 8) {
-            uint2 kv[8];
+    for (int t = warp; t < pos; t += nw) {
+        const __half *kr = kcache + ((size_t)t * Hkv + kvh) * D;
+        float s = 0.f;
+        for (int i = lane; i < D; i += 32) s += q[i] * __half2float(__ldcg(kr + i));
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + u * nw;
-                if (t0 == warp) kv[u] = kpre[u];  // first batch: prefetched
-                else kv[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(kcache + ((size_t)t * Hkv + kvh) * D) + lane) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + u * nw;
-                float k4[4];
-                unpack4(kv[u], k4);
-                float s = q4.x * k4[0] + q4.y * k4[1] + q4.z * k4[2] + q4.w * k4[3];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0 && t < pos) sc[t] = s * scale;
-            }
-        }
-    } else {
-        for (int t = warp; t < pos; t += nw) {
-            const __half *kr = kcache + ((size_t)t * Hkv + kvh) * D;
-            float s = 0.f;
-            for (int i = lane; i < D; i += 32) s += q[i] * __half2float(__ldcg(kr + i));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) sc[t] = s * scale;
-        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sc[t] = s * scale;
     }
     if (warp == 0) {  // the new token, from shared memory (not the cache: no cross-CTA race)
         float s = 0.f;
@@ -769,40 +886,6 @@ rope_attention_kernel(__half *__restrict__ attn_out, const float *__restrict__ a
     }
     sum = block_sum(sum, red);
     __syncthreads();
-    if (D == 128) {
-        // output: warp w takes positions w, w + 8, ... (one 256-byte V row per load, 8 in flight), lane owns dims 4*lane..+3;
-        // the 8 partial rows are summed through shared memory
-        float o4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int t0 = warp; t0 < pos; t0 += nw * 8) {
-            uint2 vv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + u * nw;
-                if (t0 == warp) vv[u] = vpre[u];
-                else vv[u] = (t < pos) ? __ldcg(reinterpret_cast<const uint2 *>(vcache + ((size_t)t * Hkv + kvh) * D) + lane) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + u * nw;
-                if (t < pos) {
-                    float v4[4];
-                    unpack4(vv[u], v4);
-                    const float w = sc[t];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o4[e] += w * v4[e];
-                }
-            }
-        }
-        reinterpret_cast<float4 *>(part + warp * D)[lane] = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        __syncthreads();
-        if (threadIdx.x < D) {
-            float o = sc[pos] * vn[threadIdx.x];
-#pragma unroll
-            for (int w = 0; w < kAttnThreads / 32; ++w) o += part[w * D + threadIdx.x];
-            attn_out[head * D + threadIdx.x] = __float2half(o / sum);
-        }
-        return;
-    }
     // generic head size: two halves of the positions per dim, 8 loads in flight
     const int dd = threadIdx.x % D, part_id = threadIdx.x / D, nparts = (kAttnThreads / D) >= 2 ? 2 : 1;
     if (part_id < nparts) {
@@ -1190,11 +1273,31 @@ extern "C" int qp_silu_mul_had_grid_xchg(void *x_out_f16, const float *acc_local
     return check_launch("silu_mul_had_grid_xchg");
 }
 
+// scratch of the split kernel: [H] tickets (zeroed once by the caller, left zero by every launch) | [H][S][kAttnPart] partials
+static int attn_splits(int max_seq) { return (max_seq + kAttnChunk - 1) / kAttnChunk; }
+extern "C" size_t qp_rope_attention_scratch_bytes(int H, int D, int max_seq) {
+    if (D != 128 || attn_splits(max_seq) <= 1) return 0;
+    return (((size_t)H * 4 + 15) & ~(size_t)15) + (size_t)H * attn_splits(max_seq) * kAttnPart * 4;
+}
+
 extern "C" int qp_rope_attention(void *attn_out_f16, const float *acc_qkv, const void *wscale_f16, float acc_scale,
                                  const float *inv_freq, void *kcache_f16, void *vcache_f16, const int *pos_ptr, int H,
-                                 int Hkv, int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *stream) {
+                                 int Hkv, int D, int max_seq, int qvk_order, float *zero_ptr, int zero_count, void *scratch,
+                                 void *stream) {
     QP_CHECK_ARG(attn_out_f16 && acc_qkv && wscale_f16 && inv_freq && kcache_f16 && vcache_f16 && pos_ptr, "NULL pointer");
     QP_CHECK_ARG(D <= 128 && D % 2 == 0 && H % Hkv == 0 && kAttnThreads % D == 0, "unsupported head geometry H=%d Hkv=%d D=%d", H, Hkv, D);
+    QP_CHECK_ARG(max_seq >= 1, "max_seq = %d", max_seq);
+    if (D == 128) {
+        const int S = attn_splits(max_seq);
+        QP_CHECK_ARG(S == 1 || scratch, "max_seq = %d needs the scratch buffer of qp_rope_attention_scratch_bytes()", max_seq);
+        QP_CHECK_ARG(S <= 65535, "max_seq = %d too large", max_seq);
+        unsigned *tickets = (unsigned *)scratch;
+        float *part = scratch ? (float *)((unsigned char *)scratch + (((size_t)H * 4 + 15) & ~(size_t)15)) : nullptr;
+        QP_CUDA(launch_pdl(rope_attention_split_kernel, dim3(H, S), dim3(kAttnThreads), 0, (cudaStream_t)stream,
+                           (__half *)attn_out_f16, acc_qkv, (const __half *)wscale_f16, acc_scale, inv_freq, (__half *)kcache_f16,
+                           (__half *)vcache_f16, pos_ptr, H, Hkv, max_seq, qvk_order, zero_ptr, zero_count, part, tickets, S));
+        return check_launch("rope_attention_split");
+    }
     const size_t smem = (size_t)(11 * D + max_seq) * 4;
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 1024, "max_seq = %d too large for the single-pass attention kernel", max_seq);
     static DeviceOnce configured;

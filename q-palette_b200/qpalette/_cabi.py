@@ -48,7 +48,8 @@ SIGNATURES = {
     "qp_silu_mul_had": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_cluster": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp],
     "qp_silu_mul_had_grid": [_vp, _vp, _vp, _f, _vp, _i, _f, _vp, _i, _vp, _vp],
-    "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "qp_rope_attention": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "qp_rope_attention_scratch_bytes": [_i, _i, _i],
     "qp_gemv_f16": [_vp, _vp, _vp, _i, _i, _vp],
     "qp_argmax": [_vp, _vp, _i, _vp, _vp],
     "qp_embed": [_vp, _vp, _vp, _i, _vp],
@@ -57,7 +58,8 @@ SIGNATURES = {
     "qp_lut_gemv_fused": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "qp_tcq_gemv_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
-_RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64, "qp_gemm_mma_scratch_bytes": ctypes.c_size_t}
+_RESTYPES = {"qp_last_error": ctypes.c_char_p, "qp_launch_count": ctypes.c_uint64, "qp_gemm_mma_scratch_bytes": ctypes.c_size_t,
+             "qp_rope_attention_scratch_bytes": ctypes.c_size_t}
 
 
 class XProd(ctypes.Structure):

@@ -237,6 +237,9 @@ class DecodeRunner:
         self.h2 = torch.zeros(H, **f16)          # ping-pong partner of h for the fused prologues
         self.x_h = torch.zeros(H, **f16)
         self.x_i = torch.zeros(I, **f16)
+        # split-KV attention: partial softmaxes + one ticket per head, shared by all layers (zeroed once; launches leave it zero)
+        nb = int(lib().qp_rope_attention_scratch_bytes(shape.num_attention_heads // world, shape.head_dim, max_seq))
+        self.attn_scratch = torch.zeros(nb, dtype=torch.uint8, device=self.dev) if nb else None
         self.region = None
         if self.p2p:
             # the four gathered buffers live in a region every peer maps; site = 4 * layer + {attn, o, act, down}
@@ -351,7 +354,7 @@ class DecodeRunner:
                 hc, ho = ho, hc
             check(L.qp_rope_attention(p(self.attn) + 2 * rank * (H // world), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq),
                                       p(ly["kc"]), p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
-                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
+                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, p(self.attn_scratch), st))
             ll = send("attn", p(self.attn) + 2 * rank * Ho, 0, self.acc_o)
             run_group([(ly["o"], 0)], self.acc_o, rank * Ho, xp(self.attn, su=ly["SU_o"], ll=ll, ll_kind=2))
             ll = send("acc_o", p(self.acc_o) + 4 * rank * Ho, 1, self.acc_ug)
@@ -412,7 +415,7 @@ class DecodeRunner:
                 hc, ho = ho, hc
             check(L.qp_rope_attention(p(self.attn), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads, sh.num_key_value_heads,
-                                      sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
+                                      sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, p(self.attn_scratch), st))
             # fused launches clear accumulators BEFORE their dependency wait: only buffers the preceding launch does not
             # touch (the attention kernel still reads acc_qkv while the o projection starts, so ug clears it instead)
             prod = xp(self.attn, su=ly["SU_o"], z2=self.acc_dn)
@@ -442,7 +445,7 @@ class DecodeRunner:
         sh, H, I = self.shape, self.H, self.I
         world, rank = self.world, self.rank
         n0 = _cabi.launch_count()
-        p = lambda t: t.data_ptr()
+        p = lambda t: t.data_ptr() if t is not None else None
         s_h, s_i, S = 1.0 / (math.sqrt(H) * 64.0), 1.0 / (math.sqrt(I) * 64.0), 64.0
         Hq, Hk, Il, Ho = H // world, self.kvd // world, I // world, H // world
         check(L.qp_embed(p(self.h), p(self.embed), p(self.token), H, st))
@@ -473,7 +476,7 @@ class DecodeRunner:
             attn_dst = p(self.attn) + 2 * rank * Hq if p2p else (p(self.attn) if world == 1 else p(self.attn_loc))
             check(L.qp_rope_attention(attn_dst, p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
                                       p(ly["vc"]), p(self.pos), sh.num_attention_heads // world,
-                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, st))
+                                      sh.num_key_value_heads // world, sh.head_dim, self.max_seq, ly.get("qvk", 0), None, 0, p(self.attn_scratch), st))
             if gather:
                 torch.distributed.all_gather_into_tensor(self.attn, self.attn_loc, group=self.pg)
             norm_had(4 * li + 0, "attn", p(self.x_h), p(self.attn), 0, None, None, 0.0, None, 0.0, p(ly["SU_o"]), H, s_h, 1,
@@ -524,10 +527,13 @@ class DecodeRunner:
                     torch.distributed.all_gather_into_tensor(full, ly[name], group=self.pg)
                     ly[name + "_full"] = full
 
-    def reset(self, token=1):
+    def reset(self, token=1, pos=0):
+        """restart decoding from `token` at position `pos` (pos > 0: the KV rows below pos are taken as they are in the cache)"""
+        if not 0 <= pos < self.max_seq:
+            raise RuntimeError(f"position {pos} outside the KV cache (max_seq={self.max_seq})")
         self.token.fill_(token)
-        self.pos.zero_()
-        self.steps_done = 0
+        self.pos.fill_(pos)
+        self.steps_done = pos
 
     def capture(self):
         self.reset()

@@ -44,4 +44,10 @@ timeit("fused_norm_had n=4096 had only", lambda st: check(L.qp_fused_norm_had(p(
 timeit("fused_norm_had n=4096 norm only", lambda st: check(L.qp_fused_norm_had(p(x_h), p(h), 1, p(acc_h), p(w_h), 64.0, p(norm), 1e-5, None, H, 1.0, 0, None, 0, st)))
 timeit("silu_mul_had I=14336", lambda st: check(L.qp_silu_mul_had(p(x_i), p(acc_ug), p(w_ug), 64.0, p(su_i), I, s_i, p(acc_h), H, st)))
 timeit("silu_mul_had I=14336 no zeroing", lambda st: check(L.qp_silu_mul_had(p(x_i), p(acc_ug), p(w_ug), 64.0, p(su_i), I, s_i, None, 0, st)))
-timeit("rope_attention pos=64", lambda st: check(L.qp_rope_attention(p(attn), p(acc_qkv), p(w_qkv), 64.0, p(inv), p(kc), p(vc), p(pos), 32, 8, 128, 256, 0, None, 0, st)))
+MAXS = 4096 + 64
+kc = torch.zeros(MAXS * 8 * 128, dtype=torch.float16, device="cuda")
+vc = torch.zeros(MAXS * 8 * 128, dtype=torch.float16, device="cuda")
+ascr = torch.zeros(int(L.qp_rope_attention_scratch_bytes(32, 128, MAXS)), dtype=torch.uint8, device="cuda")
+for ps in (16, 64, 127, 150, 512, 2048, 4096):
+    pos.fill_(ps)
+    timeit(f"rope_attention pos={ps}", lambda st: check(L.qp_rope_attention(p(attn), p(acc_qkv), p(w_qkv), 64.0, p(inv), p(kc), p(vc), p(pos), 32, 8, 128, MAXS, 0, None, 0, p(ascr), st)))
