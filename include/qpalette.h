@@ -29,6 +29,10 @@ extern "C" {
 
 /* flags */
 #define QP_FLAG_ACCUMULATE 1u /* GEMV: add into `out` instead of overwriting it (out must hold valid fp32 data) */
+/* GEMV prologue order, never changes the result (default: codebook fill before the programmatic-dependency wait); both were
+ * measured slower inside the decode step and are kept for A/B timing, see qp_xprod.prologue_order */
+#define QP_FLAG_DECODE_AHEAD 2u /* ... and decode every warp's first super-tile into shared memory before the wait */
+#define QP_FLAG_TABLE_LATE 4u   /* wait first, codebook fill under the L2 round trip of x */
 
 /* epilogue selector of qp_incoherent_* (fused layer ops) */
 #define QP_EPI_NONE 0
@@ -235,6 +239,10 @@ typedef struct qp_xprod {
     const void *ll;
     const unsigned *ll_epoch;
     int ll_kind;
+    /* prologue order, never changes the result.  0 (default): codebook fill before the dependency wait.  1: ... and every warp's
+     * first super-tile decoded into shared memory before the wait.  2: wait first, codebook fill under the L2 round trip of the
+     * activation loads.  1 and 2 measured slower inside the decode step and are kept for A/B timing. */
+    int prologue_order;
 } qp_xprod;
 int qp_tcq_gemv_fused(float *out, const void *codes1, const void *codes2, const qp_xprod *xp, const void *tlut_f16,
                       int M, int K, int S, int KV1, int KV2, int split_mode, int part1, void *stream);

@@ -372,6 +372,7 @@ int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
     p.ll_epoch = u->ll_epoch;
     p.ll_kind = u->ll ? u->ll_kind : 0;
     p.ll_spin_cycles = qp_spin_limit_cycles_host();
+    p.ahead = (u->prologue_order >= 0 && u->prologue_order <= 2) ? u->prologue_order : 0;
     return QP_OK;
 }
 

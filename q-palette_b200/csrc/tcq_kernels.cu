@@ -21,17 +21,20 @@
 namespace qp {
 
 #ifdef QP_PROFILE_PHASES
-// debug build only: per-CTA %globaltimer stamps of the GEMV phases (read back with qp_debug_phases)
+// debug build only: per-CTA %globaltimer stamps of the GEMV phases.  g_phase holds the last launch (qp_debug_phases); g_plog
+// is an append-only log of every CTA of every launch {M<<32|K, cta | xmode<<16 | ahead<<20, 7 stamps} (qp_debug_plog), so that
+// the launches of a whole decode step can be laid out on one timeline (tools/phase_profile_step.py)
+constexpr unsigned kPlogCap = 40000;
 __device__ unsigned long long g_phase[256][8];
-__device__ __forceinline__ void phase_stamp(int i) {
-    if (threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_phase[blockIdx.x][i] = t;
-    }
-}
-#define QP_PHASE(i) phase_stamp(i)
+__device__ unsigned long long g_plog[kPlogCap][9];
+__device__ unsigned g_plog_n;
+#define QP_PHASE_DECL unsigned long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define QP_PHASE(i)                                                             \
+    do {                                                                        \
+        if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_[i])); \
+    } while (0)
 #else
+#define QP_PHASE_DECL
 #define QP_PHASE(i)
 #endif
 
@@ -168,16 +171,40 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     const int lane = threadIdx.x & 31;
     const int warp = warp_in_cta();
     const int gwarp = blockIdx.x * kTcqWarps + warp;
+    QP_PHASE_DECL;
     QP_PHASE(0);
-    // this warp's contiguous run of each part (a CTA's runs are adjacent: the CTA streams one contiguous byte range)
-    const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
-    // the HBM stream starts first (it has the longest latency and depends on nothing), then the codebook loads: both round
-    // trips run under the rest of the prologue
-    uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
-    gemv2_prefetch<KVA>(segA, runA, rawA);
+    // the codebook loads go first (nothing to compute for them), then the HBM stream of this warp's contiguous run of each part
+    // (a CTA's runs are adjacent: the CTA streams one contiguous byte range): both round trips run under the rest of the prologue
     TcqTableRegs<S> tregs;
     tcq_table_load<S>(tregs, tlut);
+    const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
+    uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
+    gemv2_prefetch<KVA>(segA, runA, rawA);
     QP_PHASE(1);
+    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
+    // Order of the rest of the prologue (prod.ahead, a host hint that never changes the result):
+    //  0 (default): codebook fill before the dependency wait.
+    //  1: ... and each warp's first super-tile decoded into shared memory before the wait (decoding needs the codebook, not x).
+    //  2: wait first, then the x loads, the codebook fill under their L2 round trip.
+    // 1 and 2 were built for the decode step and measured SLOWER there (profiles/r02_prologue_orders.log): the
+    // critical CTAs of a launch are the ones whose SM was still held by the preceding kernel -- they start when the dependency is
+    // about to resolve and have nothing to overlap the extra work with (1), and for every other CTA the fill is free before the
+    // wait but not after it (2).
+    const int order = prod.ahead;
+    uint4 *pre_dst = reinterpret_cast<uint4 *>(smem + TcqTable<S>::kBytes + (size_t)K * bs * 2 + (XMODE != 0 ? (size_t)K * 4 : 0)) +
+                     warp * (4 * 32);
+    bool predecoded = false;
+    auto work_ahead = [&]() {
+        if (order == 2) return;
+        tcq_table_store<S>(tab, tregs);
+        if (order == 1) {
+            __syncthreads();
+            predecoded = gemv2_predecode<TcqDecoder<KVA, S>>(segA, runA, rawA, tab_addr_lane, pre_dst);
+        }
+    };
+    auto fill_table = [&]() {
+        if (order == 2) tcq_table_store<S>(tab, tregs);
+    };
     if constexpr (XMODE != 0) {
         float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
         // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
@@ -186,41 +213,50 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
             XPre<CH> pre;
             xp_preload<CH>(pre, prod, K);
             xp_zero(prod);
-            tcq_table_store<S>(tab, tregs);
+            work_ahead();
             QP_PHASE(2);
             pdl_wait();  // x (and out) are produced by the preceding kernel
             QP_PHASE(3);
-            produce_x<CH, XMODE == 2>(xs, xscratch, red, prod, K, pre);
+            produce_x<CH, XMODE == 2>(xs, xscratch, red, prod, K, pre, fill_table);
         };
         if (((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
         else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
     } else {
-        tcq_table_store<S>(tab, tregs);
+        work_ahead();
         QP_PHASE(2);
         pdl_wait();  // x (and out) are produced by the preceding kernel
         QP_PHASE(3);
-        stage_x(xs, x32, K, bs);
+        stage_x(xs, x32, K, bs, fill_table);
     }
     __syncthreads();
     QP_PHASE(4);
     pdl_launch_dependents();
 
-    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
     const uint32_t xs_addr = smem_u32(xs);
+    const uint32_t pre_addr = predecoded ? smem_u32(pre_dst) : 0u;
     if constexpr (KVB == 0) {
-        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {});
+        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {}, pre_addr);
     } else {
         const WarpRun2 runB = warp_run2(segB, splitB, gwarp);
         uint32_t rawB[kGemv2Depth][TcqGeom<KVB>::kRawWords];
         // the second part's first loads are issued while the first part's tail drains
         gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
-                                      [&] { gemv2_prefetch<KVB>(segB, runB, rawB); });
-        gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {});
+                                      [&] { gemv2_prefetch<KVB>(segB, runB, rawB); }, pre_addr);
+        gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {}, 0u);
     }
 #ifdef QP_PROFILE_PHASES
     QP_PHASE(5);  // thread 0's warp done
     __syncthreads();
     QP_PHASE(6);  // whole CTA done
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 7; ++i) g_phase[blockIdx.x][i] = ph_[i];
+        const unsigned k = atomicAdd(&g_plog_n, 1u);
+        if (k < kPlogCap) {
+            g_plog[k][0] = ((unsigned long long)M << 32) | (unsigned)K;
+            g_plog[k][1] = blockIdx.x | (XMODE << 16) | (prod.ahead << 20);
+            for (int i = 0; i < 7; ++i) g_plog[k][2 + i] = ph_[i];
+        }
+    }
 #endif
 }
 
@@ -329,9 +365,14 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     const bool fused = prod.mode != 0;
     auto kern = prod.mode == 0 ? tcq_gemv_kernel<KVA, KVB, S, 0>
                                : (prod.mode == 1 ? tcq_gemv_kernel<KVA, KVB, S, 1> : tcq_gemv_kernel<KVA, KVB, S, 2>);
-    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
+    size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the shared-memory budget of the %s GEMV", K,
                  fused ? "fused-prologue" : "plain");
+    XProd prod_l = prod;  // the work-ahead order needs room for one decoded super-tile per warp
+    if (prod_l.ahead == 1) {
+        if (smem + kGemvPredecodeBytes <= (size_t)kMaxSmem - 256) smem += kGemvPredecodeBytes;
+        else prod_l.ahead = 0;
+    }
     static DeviceOnce configured[3];
     if (configured[prod.mode].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
@@ -340,7 +381,7 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     const int nwarps = nctas * kTcqWarps;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
                        make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
-                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod_l));
     return check_launch("tcq_gemv");
 }
 
@@ -510,6 +551,7 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     for (int b0 = 0; b0 < bs; b0 += chunk) {
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
         XProd none = {};
+        none.ahead = (flags & QP_FLAG_DECODE_AHEAD) ? 1 : ((flags & QP_FLAG_TABLE_LATE) ? 2 : 0);
         rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, none, st);
         if (rc != QP_OK) return rc;
     }
@@ -569,6 +611,17 @@ extern "C" int qp_debug_xphases(unsigned long long *host_out /* [256][8] */) {
 }
 extern "C" int qp_debug_phases(unsigned long long *host_out /* [256][8] */) {
     QP_CUDA(cudaMemcpyFromSymbol(host_out, qp::g_phase, sizeof(unsigned long long) * 256 * 8));
+    return QP_OK;
+}
+// copies the log (up to `cap` records of 9 words), returns the record count in *n and clears the log
+extern "C" int qp_debug_plog(unsigned long long *host_out, unsigned cap, unsigned *n) {
+    unsigned cnt = 0, zero = 0;
+    QP_CUDA(cudaMemcpyFromSymbol(&cnt, qp::g_plog_n, sizeof(unsigned)));
+    if (cnt > qp::kPlogCap) cnt = qp::kPlogCap;
+    if (cnt > cap) cnt = cap;
+    if (cnt) QP_CUDA(cudaMemcpyFromSymbol(host_out, qp::g_plog, sizeof(unsigned long long) * 9 * cnt));
+    QP_CUDA(cudaMemcpyToSymbol(qp::g_plog_n, &zero, sizeof(unsigned)));
+    *n = cnt;
     return QP_OK;
 }
 #endif

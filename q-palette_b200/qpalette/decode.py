@@ -16,6 +16,7 @@ are all-gathered with NCCL at the four layer boundaries.
 """
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -103,12 +104,14 @@ class _Proj:
         self.weight_bytes = self.codes1.numel() * self.codes1.element_size() + \
             (self.codes2.numel() * self.codes2.element_size() if self.codes2 is not None else 0)
 
-    def launch(self, out_ptr, x_ptr, stream):
+    def launch(self, out_ptr, x_ptr, stream, ahead=0):
+        """ahead: prologue order of include/qpalette.h (0 default, 1 decode ahead, 2 table late; A/B timing only)"""
         L = lib()
         if self.kind in ("tcq_ldlq", "combt_ldlq"):
+            hint = {0: 0, 1: _cabi.FLAG_DECODE_AHEAD, 2: _cabi.FLAG_TABLE_LATE}[ahead]
             check(L.qp_tcq_gemv(out_ptr, self.codes1.data_ptr(), self.codes2.data_ptr() if self.codes2 is not None else None,
                                 x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.S, self.KV1, self.KV2, self.split,
-                                self.part1, FLAG_ACCUMULATE, stream))
+                                self.part1, FLAG_ACCUMULATE | hint, stream))
         elif self.simt:
             check(L.qp_simt_gemv(out_ptr, self.codes1.data_ptr(), x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.bits,
                                  self.vec, 1, stream))
@@ -403,6 +406,11 @@ class DecodeRunner:
                 if i != lead:
                     proj.launch(p(acc_buf) + 4 * off, p(x_buf), st)
 
+        # GEMV prologue orders (include/qpalette.h, qp_xprod.prologue_order), for A/B timing only: QP_AHEAD_MODE = late | ahead |
+        # mixed (qkv / ug, which follow a GEMV: late; o / down, which follow a short kernel: decode ahead).  The default order
+        # (codebook fill before the dependency wait) measured fastest: profiles/r02_prologue_orders.log
+        mode = os.environ.get("QP_AHEAD_MODE", "old")
+        after_gemv, after_glue = {"mixed": (2, 1), "old": (0, 0), "late": (2, 2), "ahead": (1, 1)}[mode]
         prev = None
         for ly in self.layers:
             if prev is None:
@@ -410,6 +418,7 @@ class DecodeRunner:
             else:
                 prod = xp(hc, h_out=ho, acc=self.acc_dn, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"],
                           z1=self.acc_o, z2=self.acc_ug)
+            prod.prologue_order = after_gemv
             run_group(ly["qkv"], self.acc_qkv, prod, self.x_h)
             if prev is not None:
                 hc, ho = ho, hc
@@ -419,8 +428,10 @@ class DecodeRunner:
             # fused launches clear accumulators BEFORE their dependency wait: only buffers the preceding launch does not
             # touch (the attention kernel still reads acc_qkv while the o projection starts, so ug clears it instead)
             prod = xp(self.attn, su=ly["SU_o"], z2=self.acc_dn)
+            prod.prologue_order = after_glue
             run_group([(ly["o"], 0)], self.acc_o, prod, self.x_h)
             prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"], z1=self.acc_qkv)
+            prod.prologue_order = after_gemv
             run_group(ly["ug"], self.acc_ug, prod, self.x_h)
             hc, ho = ho, hc
             if self.silu_grid:  # one thread-block cluster, blocks exchanged through distributed shared memory
@@ -428,7 +439,7 @@ class DecodeRunner:
                                                 st))
             else:
                 check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
-            ly["down"].launch(p(self.acc_dn), p(self.x_i), st)
+            ly["down"].launch(p(self.acc_dn), p(self.x_i), st, ahead=after_glue)
             prev = ly
         check(L.qp_fused_norm_had(p(self.xf), p(hc), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
                                   sh.rms_norm_eps, None, H, 1.0, 0, None, 0, st))
