@@ -2,6 +2,7 @@
 #pragma once
 #include "qp_common.cuh"
 #include "tcq_bits.cuh"
+#include "run_split.cuh"
 
 namespace qp {
 
@@ -138,18 +139,6 @@ constexpr int kGemvCtasPerSM = QP_GEMV_CTAS;    // experiments: 2 CTAs of 384 th
 constexpr int kGemvThreads = QP_GEMV_THREADS;   // one CTA per SM (the lane-replicated codebook takes 128 KiB)
 constexpr int kGemvWarps = kGemvThreads / 32;
 
-// even split of T work items over the grid's warps, computed on the host: warp w owns
-// [w*base + min(w, rem), ... + base + (w < rem))
-struct RunSplit {
-    unsigned base, rem;
-};
-inline RunSplit make_split(long T, int nwarps) { return RunSplit{(unsigned)(T / nwarps), (unsigned)(T % nwarps)}; }
-__device__ __forceinline__ void split_range(const RunSplit s, int w, unsigned &lo, unsigned &hi) {
-    const unsigned uw = (unsigned)w;
-    lo = uw * s.base + (uw < s.rem ? uw : s.rem);
-    hi = lo + s.base + (uw < s.rem ? 1u : 0u);
-}
-
 // lane-replicated table fill: `rows` slots of 128 bytes, slot r = 32 copies of value(r).  8 lanes cover a slot with one
 // 16-byte store each, so a warp store instruction writes 4 consecutive slots (512 contiguous bytes, conflict-free).
 template <class F>
@@ -246,6 +235,12 @@ __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __hal
 #ifndef QP_GEMV2_DEPTH
 #define QP_GEMV2_DEPTH 3
 #endif
+#ifndef QP_REFILL_LATE
+#define QP_REFILL_LATE 1
+#endif
+#ifndef QP_STEADY_LOOP
+#define QP_STEADY_LOOP 0
+#endif
 constexpr int kGemv2Depth = QP_GEMV2_DEPTH;
 
 struct WarpRun2 {
@@ -253,9 +248,9 @@ struct WarpRun2 {
     int n;        // super-tiles of this warp
     int mh, kh;   // strip / column of the first one
 };
-__device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSplit split, int gwarp) {
+__device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSplit split, int cta, int warp) {
     unsigned lo, hi;
-    split_range(split, gwarp, lo, hi);
+    split_range_cta(split, cta, warp, kGemvWarps, lo, hi);
     WarpRun2 r;
     r.lo = lo;
     r.n = (int)(hi - lo);
@@ -408,14 +403,35 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
         i = 1;
     }
     const uint32_t *p = gemv2_lane_ptr<E>(seg, run) + (i + D) * SBw;  // refill source of ring slot 0
-    // main loop: D valid steps per trip; a refill is predicated on its super-tile being inside the run
+    // main loop: D valid steps per trip.  Steady part: every refill lies inside the run (plain loads, no predicate); the last
+    // full trips predicate each refill on its super-tile being inside the run
+#if QP_STEADY_LOOP
+    for (; i + 2 * D <= n; i += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            uint32_t P[G::kWords];
+            tcq_align<E>(raw[d], bitoff, P);
+            gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+            pack_load_raw<E>(raw[d], p + d * SBw);
+            advance();
+        }
+        p += D * SBw;
+    }
+#endif
     for (; i + D <= n; i += D) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             uint32_t P[G::kWords];
-            tcq_align<E>(raw[d], bitoff, P);  // the slot's registers are dead after this: the refill lands in them
+            tcq_align<E>(raw[d], bitoff, P);
+#if QP_REFILL_LATE
+            // the refill is issued AFTER the decode has read the slot: issued before it (0), the in/out asm operands force a copy
+            // of the payload words (5 IMAD.MOV per super-tile in the SASS of the KV = 6 loop)
+            gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+            pack_load_raw_pred<E>(raw[d], p + d * SBw, i + d + D < n);
+#else
             pack_load_raw_pred<E>(raw[d], p + d * SBw, i + d + D < n);
             gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+#endif
             advance();
         }
         p += D * SBw;

@@ -110,6 +110,9 @@ __device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *_
     tcq_table_store<S>(tab, t);
 }
 
+#ifndef QP_HASH_RUNTIME_MUL
+#define QP_HASH_RUNTIME_MUL 0  // measured: 494.9 vs 496.1 tok/s (profiles/r02_loop_variants.log)
+#endif
 template <int S>
 __device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_lane, uint32_t u) {
     using T = TcqTable<S>;
@@ -118,6 +121,12 @@ __device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_lane, uint32_t u) {
 #ifdef QP_HASH_ADD
     const uint32_t t0 = tcq_hash(u);
     const uint32_t ts = (T::kShift == 1) ? (t0 + t0) : (t0 << T::kShift);
+#elif QP_HASH_RUNTIME_MUL
+    // 2^kShift as a value ptxas cannot fold (gridDim.y == 1, a uniform register): with a literal it rewrites the expression to
+    // u*u + u followed by a doubling and picks the pipe of the doubling itself -- IADD3 on the alu pipe for 10 of the 16 lookups
+    // in the fused-prologue instantiation (alu 65 vs fma 24 instructions per super-tile, both pipes half rate)
+    const uint32_t c = gridDim.y << T::kShift;
+    const uint32_t ts = u * (u * c + c);
 #else
     const uint32_t ts = u * (u * (1u << T::kShift) + (1u << T::kShift));
 #endif
@@ -177,7 +186,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     // (a CTA's runs are adjacent: the CTA streams one contiguous byte range): both round trips run under the rest of the prologue
     TcqTableRegs<S> tregs;
     tcq_table_load<S>(tregs, tlut);
-    const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
+    const WarpRun2 runA = warp_run2(segA, splitA, (int)blockIdx.x, warp);
     uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
     gemv2_prefetch<KVA>(segA, runA, rawA);
     QP_PHASE(1);
@@ -237,7 +246,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     if constexpr (KVB == 0) {
         gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {}, pre_addr);
     } else {
-        const WarpRun2 runB = warp_run2(segB, splitB, gwarp);
+        const WarpRun2 runB = warp_run2(segB, splitB, (int)blockIdx.x, warp);
         uint32_t rawB[kGemv2Depth][TcqGeom<KVB>::kRawWords];
         // the second part's first loads are issued while the first part's tail drains
         gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
@@ -380,7 +389,8 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     const int nctas = sm_count() * kGemvCtasPerSM;
     const int nwarps = nctas * kTcqWarps;
     QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
-                       make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
+                       make_split_skewed((long)L.a.strips * L.a.ksuper, nctas, prod.late_ctas, prod.late_permille),
+                       make_split_skewed((long)L.b.strips * L.b.ksuper, nctas, prod.late_ctas, prod.late_permille, /*flip=*/true),
                        out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod_l));
     return check_launch("tcq_gemv");
 }
@@ -552,6 +562,8 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
         XProd none = {};
         none.ahead = (flags & QP_FLAG_DECODE_AHEAD) ? 1 : ((flags & QP_FLAG_TABLE_LATE) ? 2 : 0);
+        none.late_ctas = (int)((flags >> 8) & 0xffu);           // QP_FLAG_SKEW(ctas, permille)
+        none.late_permille = (int)((flags >> 16) & 0x3ffu);
         rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, none, st);
         if (rc != QP_OK) return rc;
     }

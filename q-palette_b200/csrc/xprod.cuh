@@ -51,6 +51,9 @@ struct XProd {
     unsigned long long ll_spin_cycles;  // 0 = poll forever
     // prologue order of the GEMV kernels (also read in mode 0), see tcq_gemv_kernel: 0 table first, 1 decode ahead, 2 table late
     int ahead;
+    // work split of the GEMV launch (gemv_common.cuh, make_split_skewed): the last late_ctas CTAs get late_permille / 1000 of the
+    // others' share; 0 / 1000 = even split
+    int late_ctas, late_permille;
 };
 
 // LL entries are read at L2 (ld.volatile), where the peers' NVLink stores land; an 8-byte {data, flag} half of an entry is

@@ -59,6 +59,20 @@ for gi, (a, b) in enumerate(groups):
     rows.append((int(M[a]), int(K[a]), int(ahead[a]), b - a, int(g[:, 0].min() - ref), med(0), int(g[:, 0].max() - ref), med(2), med(3),
                  int(g[:, 3].max() - ref), med(4), int(g[:, 4].max() - ref), med(6), int(g[:, 6].max() - ref),
                  int(np.median(g[:, 6] - g[:, 4]))))
+    if gi >= len(groups) - 5:  # which CTAs start late, and do the late starters finish last?
+        cta = rec[a:b, 1] & 0xFFFF
+        o_ = np.argsort(g[:, 0])
+        late = o_[-40:]
+        print(f"launch {gi} {int(M[a])}x{int(K[a])}: latest 40 starters (cta:start_ns:done_ns rel. to first start): "
+              + " ".join(f"{int(cta[j])}:{int(g[j, 0] - g[:, 0].min())}:{int(g[j, 6] - g[:, 0].min())}" for j in late))
+        fin = np.argsort(g[:, 6])[-24:]
+        z0 = g[:, 0].min()
+        print("   latest 24 finishers (cta:start:wait_done:x_staged:done): "
+              + " ".join(f"{int(cta[j])}:{int(g[j, 0] - z0)}:{int(g[j, 3] - z0)}:{int(g[j, 4] - z0)}:{int(g[j, 6] - z0)}" for j in fin))
+        print(f"   median (start, wait_done, x_staged, done) = {int(np.median(g[:, 0]) - z0)} {int(np.median(g[:, 3]) - z0)} "
+              f"{int(np.median(g[:, 4]) - z0)} {int(np.median(g[:, 6]) - z0)}")
+        print(f"   median start of cta < 100: {int(np.median(g[cta < 100, 0] - g[:, 0].min()))}; corr(cta index, start) = "
+              f"{np.corrcoef(cta, g[:, 0] - g[:, 0].min())[0, 1]:.2f}; corr(start, done) = {np.corrcoef(g[:, 0], g[:, 6])[0, 1]:.2f}")
     prev_end = g[:, 6].max()
 print("times in ns relative to the PREVIOUS GEMV launch's last CTA end")
 print(f"{'M':>6} {'K':>6} ah ctas | start min/med/max      | prework med | wait done med/max | x staged med/max | cta done med/max | loop med")
