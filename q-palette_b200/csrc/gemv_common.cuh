@@ -139,6 +139,25 @@ constexpr int kGemvCtasPerSM = QP_GEMV_CTAS;    // experiments: 2 CTAs of 384 th
 constexpr int kGemvThreads = QP_GEMV_THREADS;   // one CTA per SM (the lane-replicated codebook takes 128 KiB)
 constexpr int kGemvWarps = kGemvThreads / 32;
 
+// work split of a GEMV launch (run_split.cuh) for its one or two parts.  Default: ONE level over all warps of the grid -- the
+// remainder goes to the first warps, i.e. to the CTAs that are dispatched first and (under programmatic dependent launch) start
+// first.  The two-level split (equal CTA loads, second part's remainder flipped) is the textbook-balanced one and measured
+// SLOWER in the decode step, with or without a smaller share for the late CTAs (482 / 486 vs 488 tok/s on one box,
+// profiles/r02_split_policies.log): what the flat split gives the early starters is what they have time for.
+#ifndef QP_SPLIT_TWO_LEVEL
+#define QP_SPLIT_TWO_LEVEL 0
+#endif
+static inline void gemv_splits(RunSplit &sa, RunSplit &sb, long TA, long TB, int nctas, int late_ctas, int late_permille) {
+#if QP_SPLIT_TWO_LEVEL
+    sa = make_split_skewed(TA, nctas, late_ctas, late_permille);
+    sb = make_split_skewed(TB, nctas, late_ctas, late_permille, /*flip=*/true);
+#else
+    sa = make_split_skewed(TA, nctas * kGemvWarps, late_ctas * kGemvWarps, late_permille);
+    sb = make_split_skewed(TB, nctas * kGemvWarps, late_ctas * kGemvWarps, late_permille);
+    sa.flat = sb.flat = 1u;
+#endif
+}
+
 // lane-replicated table fill: `rows` slots of 128 bytes, slot r = 32 copies of value(r).  8 lanes cover a slot with one
 // 16-byte store each, so a warp store instruction writes 4 consecutive slots (512 contiguous bytes, conflict-free).
 template <class F>

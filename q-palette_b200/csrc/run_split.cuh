@@ -6,24 +6,25 @@
 namespace qp {
 
 // Split of T work items (super-tiles in flat [strip][column] order) into contiguous ranges, computed on the host.
-//  * one level (split_range): unit u of `units` owns base (+1 for `rem` of them) items.  Used CTA-granular by the batched GEMM and
-//    warp-granular by the dequantise kernels.
-//  * two levels (split_range_cta, the GEMV kernels): the items are first dealt to the CTAs, then a CTA's range to its warps, so
-//    that every CTA carries the same number of super-tiles (+-1).  A flat split over all warps hands the remainder to the FIRST
-//    warps of the grid: at 4096x14336 tcomb_6_7 (two parts of 28 672 super-tiles over 3 552 warps) CTAs 0..10 got 18 super-tiles
-//    per warp and all others 16, and finished 0.8 us after them in the decode step (profiles/r02_step_timeline_balance.log).
-//  * flip: the +1 items go to the LAST units (and the last warps of a CTA) instead of the first: the second part of a two-rate
-//    layer uses it so that nobody gets the extra item of both parts.
-//  * skew: the CTAs from w2 on (the highest indices) form a second class with a smaller share.  CTAs are dispatched in index
+//  * one level (split_range): unit u of `units` owns base (+1 for `rem` of them) items.  CTA-granular in the batched GEMM,
+//    warp-granular in the dequantise kernels and -- with flat = 1, the default -- in the GEMV kernels.
+//  * two levels (split_range_cta with flat = 0): the items are first dealt to the CTAs, then a CTA's range to its warps, so that
+//    every CTA carries the same number of super-tiles (+-1); `flip` sends the +1 items to the LAST units so that the second part
+//    of a two-rate layer does not hand its remainder to the same CTAs as the first.  Built because the flat split looked
+//    unbalanced (at 4096x14336 tcomb_6_7 CTAs 0..10 get 18 super-tiles per warp, all others 16, and finish 0.8 us after them) --
+//    and measured slower: the first CTAs are also the first to start (gemv_common.cuh, gemv_splits).
+//  * skew: the units from w2 on (the highest indices) form a second class with a smaller share.  CTAs are dispatched in index
 //    order, so when the preceding kernel still holds some SMs (a GEMV CTA takes a whole SM) it is exactly the LAST CTAs of the
-//    grid that start late: after the 7-CTA SiLU cluster CTAs 141..147 of down_proj start 3.3 us after the others.
+//    grid that start late: after the 7-CTA SiLU cluster CTAs 141..147 of down_proj start 3.3 us after the others.  Worth
+//    +-0.2 % in the decode step on top of the flat split; off by default (qp_xprod.late_ctas).
 struct RunSplit {
     unsigned base, rem;          // class 1: units [0, w2)
     unsigned w2, base2, rem2;    // class 2: units [w2, units), first item off2
     unsigned off2, units, flip;
+    unsigned flat;               // GEMV kernels: the units are the grid's warps (one level), not its CTAs
 };
 inline RunSplit make_split(long T, int units, bool flip = false) {
-    return RunSplit{(unsigned)(T / units), (unsigned)(T % units), (unsigned)units, 0u, 0u, (unsigned)T, (unsigned)units, flip ? 1u : 0u};
+    return RunSplit{(unsigned)(T / units), (unsigned)(T % units), (unsigned)units, 0u, 0u, (unsigned)T, (unsigned)units, flip ? 1u : 0u, 0u};
 }
 // the last late_units units get `permille` / 1000 of the others' share
 inline RunSplit make_split_skewed(long T, int units, int late_units, int permille, bool flip = false) {
@@ -32,7 +33,7 @@ inline RunSplit make_split_skewed(long T, int units, int late_units, int permill
     const long T2 = (long)((double)T * wl / (we + wl)), T1 = T - T2;
     const long n1 = units - late_units, n2 = late_units;
     return RunSplit{(unsigned)(T1 / n1), (unsigned)(T1 % n1), (unsigned)n1, (unsigned)(T2 / n2), (unsigned)(T2 % n2), (unsigned)T1,
-                    (unsigned)units, flip ? 1u : 0u};
+                    (unsigned)units, flip ? 1u : 0u, 0u};
 }
 // unit v of n: offset and count when `base` items each, one more for `rem` of them (the first, or the last when flip)
 QP_HD void split_unit(unsigned base, unsigned rem, unsigned n, unsigned v, unsigned flip, unsigned &lo, unsigned &cnt) {
@@ -59,6 +60,10 @@ QP_HD void split_range(const RunSplit s, int u, unsigned &lo, unsigned &hi) {
 }
 // two levels: range of warp `warp` (of `warps`) inside CTA `cta`'s range
 QP_HD void split_range_cta(const RunSplit s, int cta, int warp, int warps, unsigned &lo, unsigned &hi) {
+    if (s.flat) {
+        split_range(s, cta * warps + warp, lo, hi);
+        return;
+    }
     unsigned clo, chi, l, c;
     split_range(s, cta, clo, chi);
     const unsigned n = chi - clo;

@@ -388,9 +388,9 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     }
     const int nctas = sm_count() * kGemvCtasPerSM;
     const int nwarps = nctas * kTcqWarps;
-    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
-                       make_split_skewed((long)L.a.strips * L.a.ksuper, nctas, prod.late_ctas, prod.late_permille),
-                       make_split_skewed((long)L.b.strips * L.b.ksuper, nctas, prod.late_ctas, prod.late_permille, /*flip=*/true),
+    RunSplit sa, sb;
+    gemv_splits(sa, sb, (long)L.a.strips * L.a.ksuper, (long)L.b.strips * L.b.ksuper, nctas, prod.late_ctas, prod.late_permille);
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b, sa, sb,
                        out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod_l));
     return check_launch("tcq_gemv");
 }
