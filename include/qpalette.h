@@ -29,13 +29,6 @@ extern "C" {
 
 /* flags */
 #define QP_FLAG_ACCUMULATE 1u /* GEMV: add into `out` instead of overwriting it (out must hold valid fp32 data) */
-/* GEMV prologue order, never changes the result (default: codebook fill before the programmatic-dependency wait); both were
- * measured slower inside the decode step and are kept for A/B timing, see qp_xprod.prologue_order */
-#define QP_FLAG_DECODE_AHEAD 2u /* ... and decode every warp's first super-tile into shared memory before the wait */
-#define QP_FLAG_TABLE_LATE 4u   /* wait first, codebook fill under the L2 round trip of x */
-/* GEMV work split, never changes the result beyond the fp32 summation order: the last `ctas` CTAs of the grid get permille / 1000
- * of the others' share (see qp_xprod.late_ctas); 0 = even split */
-#define QP_FLAG_SKEW(ctas, permille) ((((unsigned)(ctas)) & 0xffu) << 8 | (((unsigned)(permille)) & 0x3ffu) << 16)
 
 /* epilogue selector of qp_incoherent_* (fused layer ops) */
 #define QP_EPI_NONE 0
@@ -242,14 +235,6 @@ typedef struct qp_xprod {
     const void *ll;
     const unsigned *ll_epoch;
     int ll_kind;
-    /* prologue order, never changes the result.  0 (default): codebook fill before the dependency wait.  1: ... and every warp's
-     * first super-tile decoded into shared memory before the wait.  2: wait first, codebook fill under the L2 round trip of the
-     * activation loads.  1 and 2 measured slower inside the decode step and are kept for A/B timing. */
-    int prologue_order;
-    /* work split of the launch: CTAs are dispatched in index order, so when the preceding kernel of a programmatic-dependent-
-     * launch chain still holds SMs (a GEMV CTA needs a whole SM) the LAST CTAs of the grid start late and the launch ends with
-     * them.  The last late_ctas CTAs get late_permille / 1000 of the others' share of super-tiles.  0 / 0 = even split. */
-    int late_ctas, late_permille;
 } qp_xprod;
 int qp_tcq_gemv_fused(float *out, const void *codes1, const void *codes2, const qp_xprod *xp, const void *tlut_f16,
                       int M, int K, int S, int KV1, int KV2, int split_mode, int part1, void *stream);

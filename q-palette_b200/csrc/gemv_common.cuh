@@ -2,7 +2,6 @@
 #pragma once
 #include "qp_common.cuh"
 #include "tcq_bits.cuh"
-#include "run_split.cuh"
 
 namespace qp {
 
@@ -63,43 +62,12 @@ __device__ __forceinline__ void coop_copy_words(uint32_t *dst, const uint32_t *_
 // conflict-free store fed by a 4-byte gather, whose 25 % sector efficiency costs more L1 request cycles than it saves).
 // x is produced by the preceding kernel, which may still overlap this one's prologue (programmatic dependent launch): it is
 // read at L2 (ld.global.cg), not through the non-coherent L1 path.
-// `mid` runs once between the first round's load issue and its stores: the kernels put the codebook's shared-memory fill
-// there, under the L2 round trip of x.
-template <class Mid>
-__device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict__ x32, int K, int bs, Mid mid) {
+__device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict__ x32, int K, int bs) {
     const int kq = K / 8;            // uint4 per batch row
     const int total = bs * kq;       // uint4 to move
     const uint4 *x4 = reinterpret_cast<const uint4 *>(x32);
     constexpr int U = 4;
-    auto scatter = [&](int i, const uint4 v) {
-        int n = 0, j = i;    // j = uint4 index inside row n
-        if (bs != 1) {
-            n = i / kq;
-            j = i - n * kq;
-        }
-        const int kh = j >> 2, part = j & 3;      // part = which 4-word group of the 16-word column block
-        const int kl = part >> 1, b = part & 1;
-        uint32_t *d = xs + ((kh * bs + n) * 16 + kl * 2 + b);
-        d[0] = v.x;   // q = 0
-        d[4] = v.y;   // q = 1
-        d[8] = v.z;   // q = 2
-        d[12] = v.w;  // q = 3
-    };
-    {   // first round, peeled
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = threadIdx.x + u * blockDim.x;
-            v[u] = (i < total) ? __ldcg(x4 + i) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        mid();
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = threadIdx.x + u * blockDim.x;
-            if (i < total) scatter(i, v[u]);
-        }
-    }
-    for (int base = threadIdx.x + U * blockDim.x; base < total; base += U * blockDim.x) {
+    for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
         uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -109,12 +77,22 @@ __device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * blockDim.x;
-            if (i < total) scatter(i, v[u]);
+            if (i < total) {
+                int n = 0, j = i;    // j = uint4 index inside row n
+                if (bs != 1) {
+                    n = i / kq;
+                    j = i - n * kq;
+                }
+                const int kh = j >> 2, part = j & 3;      // part = which 4-word group of the 16-word column block
+                const int kl = part >> 1, b = part & 1;
+                uint32_t *d = xs + ((kh * bs + n) * 16 + kl * 2 + b);
+                d[0] = v[u].x;   // q = 0
+                d[4] = v[u].y;   // q = 1
+                d[8] = v[u].z;   // q = 2
+                d[12] = v[u].w;  // q = 3
+            }
         }
     }
-}
-__device__ __forceinline__ void stage_x(uint32_t *xs, const uint32_t *__restrict__ x32, int K, int bs) {
-    stage_x(xs, x32, K, bs, [] {});
 }
 
 // warp index / grid-wide warp id as provably warp-uniform values (lets ptxas keep run bounds in uniform registers and
@@ -139,23 +117,16 @@ constexpr int kGemvCtasPerSM = QP_GEMV_CTAS;    // experiments: 2 CTAs of 384 th
 constexpr int kGemvThreads = QP_GEMV_THREADS;   // one CTA per SM (the lane-replicated codebook takes 128 KiB)
 constexpr int kGemvWarps = kGemvThreads / 32;
 
-// work split of a GEMV launch (run_split.cuh) for its one or two parts.  Default: ONE level over all warps of the grid -- the
-// remainder goes to the first warps, i.e. to the CTAs that are dispatched first and (under programmatic dependent launch) start
-// first.  The two-level split (equal CTA loads, second part's remainder flipped) is the textbook-balanced one and measured
-// SLOWER in the decode step, with or without a smaller share for the late CTAs (482 / 486 vs 488 tok/s on one box,
-// profiles/r02_split_policies.log): what the flat split gives the early starters is what they have time for.
-#ifndef QP_SPLIT_TWO_LEVEL
-#define QP_SPLIT_TWO_LEVEL 0
-#endif
-static inline void gemv_splits(RunSplit &sa, RunSplit &sb, long TA, long TB, int nctas, int late_ctas, int late_permille) {
-#if QP_SPLIT_TWO_LEVEL
-    sa = make_split_skewed(TA, nctas, late_ctas, late_permille);
-    sb = make_split_skewed(TB, nctas, late_ctas, late_permille, /*flip=*/true);
-#else
-    sa = make_split_skewed(TA, nctas * kGemvWarps, late_ctas * kGemvWarps, late_permille);
-    sb = make_split_skewed(TB, nctas * kGemvWarps, late_ctas * kGemvWarps, late_permille);
-    sa.flat = sb.flat = 1u;
-#endif
+// even split of T work items over the grid's warps, computed on the host: warp w owns
+// [w*base + min(w, rem), ... + base + (w < rem))
+struct RunSplit {
+    unsigned base, rem;
+};
+inline RunSplit make_split(long T, int nwarps) { return RunSplit{(unsigned)(T / nwarps), (unsigned)(T % nwarps)}; }
+__device__ __forceinline__ void split_range(const RunSplit s, int w, unsigned &lo, unsigned &hi) {
+    const unsigned uw = (unsigned)w;
+    lo = uw * s.base + (uw < s.rem ? uw : s.rem);
+    hi = lo + s.base + (uw < s.rem ? 1u : 0u);
 }
 
 // lane-replicated table fill: `rows` slots of 128 bytes, slot r = 32 copies of value(r).  8 lanes cover a slot with one
@@ -257,9 +228,6 @@ __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __hal
 #ifndef QP_REFILL_LATE
 #define QP_REFILL_LATE 1
 #endif
-#ifndef QP_STEADY_LOOP
-#define QP_STEADY_LOOP 0
-#endif
 constexpr int kGemv2Depth = QP_GEMV2_DEPTH;
 
 struct WarpRun2 {
@@ -267,9 +235,9 @@ struct WarpRun2 {
     int n;        // super-tiles of this warp
     int mh, kh;   // strip / column of the first one
 };
-__device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSplit split, int cta, int warp) {
+__device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSplit split, int gwarp) {
     unsigned lo, hi;
-    split_range_cta(split, cta, warp, kGemvWarps, lo, hi);
+    split_range(split, gwarp, lo, hi);
     WarpRun2 r;
     r.lo = lo;
     r.n = (int)(hi - lo);
@@ -345,44 +313,12 @@ __device__ __forceinline__ void gemv2_consume(const uint32_t (&P)[TcqGeom<Dec::k
     mma_16816(acc[1], frag[3][0], frag[3][1], frag[3][2], frag[3][3], xb.z, xb.w);
 }
 
-// Work-ahead order of the prologue (see tcq_gemv_kernel): decode the run's first super-tile into shared memory -- decoding needs
-// the codebook but not x -- and move the ring on by one.  dst = this warp's 2 KiB: [tile 4][lane 32] A fragments (uint4).
-// Returns whether the warp has a pre-decoded super-tile (warp-uniform).
-constexpr size_t kGemvPredecodeBytes = (size_t)kGemvWarps * 4 * 32 * 16;
-template <class Dec>
-__device__ __forceinline__ bool gemv2_predecode(const PackSegment seg, const WarpRun2 run,
-                                                uint32_t (&raw)[kGemv2Depth][TcqGeom<Dec::kE>::kRawWords], uint32_t tab_lane,
-                                                uint4 *dst) {
-    constexpr int E = Dec::kE, D = kGemv2Depth;
-    using G = TcqGeom<E>;
-    if (run.n < 1) return false;
-    const int lane = threadIdx.x & 31;
-    const int bitoff = (lane * G::kLaneBytes & 3) * 8;
-    uint32_t P[G::kWords];
-    tcq_align<E>(raw[0], bitoff, P);
-    uint32_t frag[4][4];
-    Dec::decode(P, lane, tab_lane, frag);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) dst[t * 32 + lane] = make_uint4(frag[t][0], frag[t][1], frag[t][2], frag[t][3]);
-    // ring slot d now holds super-tile d + 1 of the run; the freed slot takes super-tile D
-#pragma unroll
-    for (int d = 0; d + 1 < D; ++d)
-#pragma unroll
-        for (int i = 0; i < G::kRawWords; ++i) raw[d][i] = raw[d + 1][i];
-    pack_load_raw_pred<E>(raw[D - 1], gemv2_lane_ptr<E>(seg, run) + D * (G::kSuperBytes / 4), D < run.n);
-    __syncwarp();  // the fragments are read back by the same lanes; keeps the stores ordered before them for the compiler
-    return true;
-}
-
 // stream this warp's run of one part.  xs_addr = shared-memory address of the staged x (fragment order, see stage_x);
 // `between` runs once after the main loop, before the tail (used to issue the next part's first loads).
-// pre_addr != 0: the run's first super-tile was decoded by gemv2_predecode (shared-memory address of the warp's fragments)
-// and the ring starts at the second one.
 template <class Dec, class Between>
 __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restrict__ out, int M, int bs, uint32_t xs_addr,
                                           uint32_t tab_lane, const WarpRun2 run,
-                                          uint32_t (&raw)[kGemv2Depth][TcqGeom<Dec::kE>::kRawWords], Between between,
-                                          uint32_t pre_addr = 0u) {
+                                          uint32_t (&raw)[kGemv2Depth][TcqGeom<Dec::kE>::kRawWords], Between between) {
     constexpr int E = Dec::kE, D = kGemv2Depth;
     using G = TcqGeom<E>;
     constexpr int SBw = G::kSuperBytes / 4;  // words per super-tile
@@ -399,6 +335,7 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    const uint32_t *p = gemv2_lane_ptr<E>(seg, run) + D * SBw;  // refill source of ring slot 0
     const int n = run.n;
     int i = 0;
     auto advance = [&]() {
@@ -410,33 +347,7 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
             xa = gemv2_xbase(xs_addr, seg.ksuper0, bs);
         }
     };
-    if (pre_addr != 0u) {  // warp-uniform; implies n >= 1
-        const uint4 xb = lds_u128(xa);
-        const uint32_t fa = pre_addr + (uint32_t)lane * 16u;
-        const uint4 f0 = lds_u128(fa), f1 = lds_u128(fa + 512u), f2 = lds_u128(fa + 1024u), f3 = lds_u128(fa + 1536u);
-        mma_16816(acc[0], f0.x, f0.y, f0.z, f0.w, xb.x, xb.y);
-        mma_16816(acc[1], f1.x, f1.y, f1.z, f1.w, xb.x, xb.y);
-        mma_16816(acc[0], f2.x, f2.y, f2.z, f2.w, xb.z, xb.w);
-        mma_16816(acc[1], f3.x, f3.y, f3.z, f3.w, xb.z, xb.w);
-        advance();
-        i = 1;
-    }
-    const uint32_t *p = gemv2_lane_ptr<E>(seg, run) + (i + D) * SBw;  // refill source of ring slot 0
-    // main loop: D valid steps per trip.  Steady part: every refill lies inside the run (plain loads, no predicate); the last
-    // full trips predicate each refill on its super-tile being inside the run
-#if QP_STEADY_LOOP
-    for (; i + 2 * D <= n; i += D) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            uint32_t P[G::kWords];
-            tcq_align<E>(raw[d], bitoff, P);
-            gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
-            pack_load_raw<E>(raw[d], p + d * SBw);
-            advance();
-        }
-        p += D * SBw;
-    }
-#endif
+    // main loop: D valid steps per trip; a refill is predicated on its super-tile being inside the run
     for (; i + D <= n; i += D) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -444,7 +355,8 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
             tcq_align<E>(raw[d], bitoff, P);
 #if QP_REFILL_LATE
             // the refill is issued AFTER the decode has read the slot: issued before it (0), the in/out asm operands force a copy
-            // of the payload words (5 IMAD.MOV per super-tile in the SASS of the KV = 6 loop)
+            // of the payload words (5 IMAD.MOV per super-tile in the SASS of the KV = 6 loop; 11.58 -> 11.38 us at 4096x14336,
+            // profiles/r02_loop_variants.log)
             gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
             pack_load_raw_pred<E>(raw[d], p + d * SBw, i + d + D < n);
 #else
@@ -672,8 +584,13 @@ __device__ __forceinline__ void mma_stream(const PackSegment seg, const MmaPiece
         for (int d = 0; d < D; ++d) {
             uint32_t P[G::kWords];
             tcq_align<E>(raw[d], bitoff, P);
+#if QP_REFILL_LATE
+            mma_consume<Dec, NB>(P, xa, lane, tab_lane, acc);
+            mma_fetch<E>(r, raw[d], i + d + D < n, pc.w, jump);
+#else
             mma_fetch<E>(r, raw[d], i + d + D < n, pc.w, jump);
             mma_consume<Dec, NB>(P, xa, lane, tab_lane, acc);
+#endif
             advance();
         }
     }

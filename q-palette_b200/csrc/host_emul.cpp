@@ -8,7 +8,6 @@
 
 #include "tcq_bits.cuh"
 #include "lut_bits.cuh"
-#include "run_split.cuh"
 
 template <int KV, int T>
 static void tile_states(const uint32_t (&P)[32][TcqGeom<KV>::kWords], const uint32_t (&send)[32][4], int g,
@@ -145,37 +144,4 @@ extern "C" int qp_emul_lut_pairs(const uint8_t *buf, int M, int K, int E, uint32
         default: return -1;
     }
     return 0;
-}
-
-// work split of a GEMV launch (run_split.cuh, two levels): returns 0 when the warps' ranges tile [0, T) in (CTA, warp) order,
-// else a code; cta_min / cta_max = fewest / most items of a CTA of the first class, late_max = most items of a late CTA,
-// warp_max = most items of a warp
-extern "C" int qp_emul_split_cover(long T, int nctas, int warps_per_cta, int late_ctas, int permille, int flip, unsigned *cta_min,
-                                   unsigned *cta_max, unsigned *late_max, unsigned *warp_max) {
-    const qp::RunSplit s = qp::make_split_skewed(T, nctas, late_ctas, permille, flip != 0);
-    unsigned expect = 0;
-    *cta_min = ~0u;
-    *cta_max = *late_max = *warp_max = 0;
-    for (int c = 0; c < nctas; ++c) {
-        unsigned n = 0;
-        for (int w = 0; w < warps_per_cta; ++w) {
-            unsigned lo, hi;
-            qp::split_range_cta(s, c, w, warps_per_cta, lo, hi);
-            if (lo != expect) return 1;
-            if (hi < lo) return 2;
-            if (hi - lo > *warp_max) *warp_max = hi - lo;
-            n += hi - lo;
-            expect = hi;
-        }
-        unsigned clo, chi;
-        qp::split_range(s, c, clo, chi);
-        if (chi - clo != n) return 4;
-        if ((unsigned)c < s.w2) {
-            if (n < *cta_min) *cta_min = n;
-            if (n > *cta_max) *cta_max = n;
-        } else if (n > *late_max) {
-            *late_max = n;
-        }
-    }
-    return expect == (unsigned)T ? 0 : 3;
 }

@@ -91,7 +91,7 @@ lut_gemv_kernel(PackSegment seg, RunSplit split, float *__restrict__ out, const 
     uint32_t *lc = reinterpret_cast<uint32_t *>(smem + T::kBytes);  // compact lut copy
     uint32_t *xs = lc + lut_compact_words(E, r_single);
     const int lane = threadIdx.x & 31;
-    const WarpRun2 run = warp_run2(seg, split, (int)blockIdx.x, warp_in_cta());
+    const WarpRun2 run = warp_run2(seg, split, blockIdx.x * kGemvWarps + warp_in_cta());
     uint32_t raw[kGemv2Depth][TcqGeom<E>::kRawWords];
     gemv2_prefetch<E>(seg, run, raw);
     coop_copy_words(lc, reinterpret_cast<const uint32_t *>(lut), lut_copy_words(E, r_single));
@@ -177,10 +177,8 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
     const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2 +
                         (prod.mode ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
-    RunSplit sa, sb;
-    gemv_splits(sa, sb, (long)seg.strips * seg.ksuper, 0, sm_count(), prod.late_ctas, prod.late_permille);
     QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg,
-                       sa, out, (const uint32_t *)x, lut,
+                       make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), out, (const uint32_t *)x, lut,
                        r_single, M, K, bs, prod));
     return check_launch("lut_gemv");
 }
@@ -305,8 +303,6 @@ extern "C" int qp_lut_gemv(float *out, const void *codes, const void *x_f16, con
     for (int b0 = 0; b0 < bs; b0 += chunk) {
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
         XProd none = {};
-        none.late_ctas = (int)((flags >> 8) & 0xffu);  // QP_FLAG_SKEW(ctas, permille)
-        none.late_permille = (int)((flags >> 16) & 0x3ffu);
         rc = dispatch_lut_gemv(bits, vec_sz, seg, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, lut_f16,
                                M, K, nb, none, st);
         if (rc != QP_OK) return rc;
@@ -376,9 +372,6 @@ int qp_make_xprod(qp::XProd &p, const qp_xprod *u, int K) {
     p.ll_epoch = u->ll_epoch;
     p.ll_kind = u->ll ? u->ll_kind : 0;
     p.ll_spin_cycles = qp_spin_limit_cycles_host();
-    p.ahead = (u->prologue_order >= 0 && u->prologue_order <= 2) ? u->prologue_order : 0;
-    p.late_ctas = u->late_ctas;
-    p.late_permille = u->late_permille;
     return QP_OK;
 }
 

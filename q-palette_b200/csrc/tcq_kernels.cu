@@ -22,8 +22,8 @@ namespace qp {
 
 #ifdef QP_PROFILE_PHASES
 // debug build only: per-CTA %globaltimer stamps of the GEMV phases.  g_phase holds the last launch (qp_debug_phases); g_plog
-// is an append-only log of every CTA of every launch {M<<32|K, cta | xmode<<16 | ahead<<20, 7 stamps} (qp_debug_plog), so that
-// the launches of a whole decode step can be laid out on one timeline (tools/phase_profile_step.py)
+// is an append-only log of every CTA of every launch {M<<32|K, cta | xmode<<16, 7 stamps} (qp_debug_plog), so that the launches
+// of a whole decode step can be laid out on one timeline (tools/phase_profile_step.py)
 constexpr unsigned kPlogCap = 40000;
 __device__ unsigned long long g_phase[256][8];
 __device__ unsigned long long g_plog[kPlogCap][9];
@@ -110,9 +110,6 @@ __device__ __forceinline__ void tcq_build_table(uint32_t *tab, const uint32_t *_
     tcq_table_store<S>(tab, t);
 }
 
-#ifndef QP_HASH_RUNTIME_MUL
-#define QP_HASH_RUNTIME_MUL 0  // measured: 494.9 vs 496.1 tok/s (profiles/r02_loop_variants.log)
-#endif
 template <int S>
 __device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_lane, uint32_t u) {
     using T = TcqTable<S>;
@@ -121,12 +118,6 @@ __device__ __forceinline__ uint32_t tcq_lookup(uint32_t tab_lane, uint32_t u) {
 #ifdef QP_HASH_ADD
     const uint32_t t0 = tcq_hash(u);
     const uint32_t ts = (T::kShift == 1) ? (t0 + t0) : (t0 << T::kShift);
-#elif QP_HASH_RUNTIME_MUL
-    // 2^kShift as a value ptxas cannot fold (gridDim.y == 1, a uniform register): with a literal it rewrites the expression to
-    // u*u + u followed by a doubling and picks the pipe of the doubling itself -- IADD3 on the alu pipe for 10 of the 16 lookups
-    // in the fused-prologue instantiation (alu 65 vs fma 24 instructions per super-tile, both pipes half rate)
-    const uint32_t c = gridDim.y << T::kShift;
-    const uint32_t ts = u * (u * c + c);
 #else
     const uint32_t ts = u * (u * (1u << T::kShift) + (1u << T::kShift));
 #endif
@@ -182,38 +173,15 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
     const int gwarp = blockIdx.x * kTcqWarps + warp;
     QP_PHASE_DECL;
     QP_PHASE(0);
-    // the codebook loads go first (nothing to compute for them), then the HBM stream of this warp's contiguous run of each part
-    // (a CTA's runs are adjacent: the CTA streams one contiguous byte range): both round trips run under the rest of the prologue
-    TcqTableRegs<S> tregs;
-    tcq_table_load<S>(tregs, tlut);
-    const WarpRun2 runA = warp_run2(segA, splitA, (int)blockIdx.x, warp);
+    // this warp's contiguous run of each part (a CTA's runs are adjacent: the CTA streams one contiguous byte range)
+    const WarpRun2 runA = warp_run2(segA, splitA, gwarp);
+    // the HBM stream starts first (it has the longest latency and depends on nothing), then the codebook loads: both round
+    // trips run under the rest of the prologue
     uint32_t rawA[kGemv2Depth][TcqGeom<KVA>::kRawWords];
     gemv2_prefetch<KVA>(segA, runA, rawA);
+    TcqTableRegs<S> tregs;
+    tcq_table_load<S>(tregs, tlut);
     QP_PHASE(1);
-    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
-    // Order of the rest of the prologue (prod.ahead, a host hint that never changes the result):
-    //  0 (default): codebook fill before the dependency wait.
-    //  1: ... and each warp's first super-tile decoded into shared memory before the wait (decoding needs the codebook, not x).
-    //  2: wait first, then the x loads, the codebook fill under their L2 round trip.
-    // 1 and 2 were built for the decode step and measured SLOWER there (profiles/r02_prologue_orders.log): the
-    // critical CTAs of a launch are the ones whose SM was still held by the preceding kernel -- they start when the dependency is
-    // about to resolve and have nothing to overlap the extra work with (1), and for every other CTA the fill is free before the
-    // wait but not after it (2).
-    const int order = prod.ahead;
-    uint4 *pre_dst = reinterpret_cast<uint4 *>(smem + TcqTable<S>::kBytes + (size_t)K * bs * 2 + (XMODE != 0 ? (size_t)K * 4 : 0)) +
-                     warp * (4 * 32);
-    bool predecoded = false;
-    auto work_ahead = [&]() {
-        if (order == 2) return;
-        tcq_table_store<S>(tab, tregs);
-        if (order == 1) {
-            __syncthreads();
-            predecoded = gemv2_predecode<TcqDecoder<KVA, S>>(segA, runA, rawA, tab_addr_lane, pre_dst);
-        }
-    };
-    auto fill_table = [&]() {
-        if (order == 2) tcq_table_store<S>(tab, tregs);
-    };
     if constexpr (XMODE != 0) {
         float *xscratch = reinterpret_cast<float *>(xs + (size_t)K * bs / 2);
         // the rest of the prologue, with the x-producer's constant inputs (scales, norm weight, signs) fetched before the wait
@@ -222,36 +190,36 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
             XPre<CH> pre;
             xp_preload<CH>(pre, prod, K);
             xp_zero(prod);
-            work_ahead();
+            tcq_table_store<S>(tab, tregs);
             QP_PHASE(2);
             pdl_wait();  // x (and out) are produced by the preceding kernel
             QP_PHASE(3);
-            produce_x<CH, XMODE == 2>(xs, xscratch, red, prod, K, pre, fill_table);
+            produce_x<CH, XMODE == 2>(xs, xscratch, red, prod, K, pre);
         };
         if (((K >> 2) + kTcqThreads - 1) / kTcqThreads <= 2) finish_prologue(std::integral_constant<int, 2>{});
         else finish_prologue(std::integral_constant<int, 5>{});  // host guarantees K <= 5 * 4 * kTcqThreads
     } else {
-        work_ahead();
+        tcq_table_store<S>(tab, tregs);
         QP_PHASE(2);
         pdl_wait();  // x (and out) are produced by the preceding kernel
         QP_PHASE(3);
-        stage_x(xs, x32, K, bs, fill_table);
+        stage_x(xs, x32, K, bs);
     }
     __syncthreads();
     QP_PHASE(4);
     pdl_launch_dependents();
 
+    const uint32_t tab_addr_lane = (lane & TcqTable<S>::kLaneMask) << 2;  // the table starts the dynamic shared memory
     const uint32_t xs_addr = smem_u32(xs);
-    const uint32_t pre_addr = predecoded ? smem_u32(pre_dst) : 0u;
     if constexpr (KVB == 0) {
-        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {}, pre_addr);
+        gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA, [] {});
     } else {
-        const WarpRun2 runB = warp_run2(segB, splitB, (int)blockIdx.x, warp);
+        const WarpRun2 runB = warp_run2(segB, splitB, gwarp);
         uint32_t rawB[kGemv2Depth][TcqGeom<KVB>::kRawWords];
         // the second part's first loads are issued while the first part's tail drains
         gemv2_run<TcqDecoder<KVA, S>>(segA, out, M, bs, xs_addr, tab_addr_lane, runA, rawA,
-                                      [&] { gemv2_prefetch<KVB>(segB, runB, rawB); }, pre_addr);
-        gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {}, 0u);
+                                      [&] { gemv2_prefetch<KVB>(segB, runB, rawB); });
+        gemv2_run<TcqDecoder<KVB, S>>(segB, out, M, bs, xs_addr, tab_addr_lane, runB, rawB, [] {});
     }
 #ifdef QP_PROFILE_PHASES
     QP_PHASE(5);  // thread 0's warp done
@@ -262,7 +230,7 @@ tcq_gemv_kernel(TcqSegment segA, TcqSegment segB, RunSplit splitA, RunSplit spli
         const unsigned k = atomicAdd(&g_plog_n, 1u);
         if (k < kPlogCap) {
             g_plog[k][0] = ((unsigned long long)M << 32) | (unsigned)K;
-            g_plog[k][1] = blockIdx.x | (XMODE << 16) | (prod.ahead << 20);
+            g_plog[k][1] = blockIdx.x | (XMODE << 16);
             for (int i = 0; i < 7; ++i) g_plog[k][2 + i] = ph_[i];
         }
     }
@@ -374,24 +342,18 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     const bool fused = prod.mode != 0;
     auto kern = prod.mode == 0 ? tcq_gemv_kernel<KVA, KVB, S, 0>
                                : (prod.mode == 1 ? tcq_gemv_kernel<KVA, KVB, S, 1> : tcq_gemv_kernel<KVA, KVB, S, 2>);
-    size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
+    const size_t smem = (size_t)TcqTable<S>::kBytes + (size_t)K * bs * 2 + (fused ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the shared-memory budget of the %s GEMV", K,
                  fused ? "fused-prologue" : "plain");
-    XProd prod_l = prod;  // the work-ahead order needs room for one decoded super-tile per warp
-    if (prod_l.ahead == 1) {
-        if (smem + kGemvPredecodeBytes <= (size_t)kMaxSmem - 256) smem += kGemvPredecodeBytes;
-        else prod_l.ahead = 0;
-    }
     static DeviceOnce configured[3];
     if (configured[prod.mode].first()) {
         QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 256));
     }
     const int nctas = sm_count() * kGemvCtasPerSM;
     const int nwarps = nctas * kTcqWarps;
-    RunSplit sa, sb;
-    gemv_splits(sa, sb, (long)L.a.strips * L.a.ksuper, (long)L.b.strips * L.b.ksuper, nctas, prod.late_ctas, prod.late_permille);
-    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b, sa, sb,
-                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod_l));
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
+                       make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
+                       out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
     return check_launch("tcq_gemv");
 }
 
@@ -561,9 +523,6 @@ extern "C" int qp_tcq_gemv(float *out, const void *codes1, const void *codes2, c
     for (int b0 = 0; b0 < bs; b0 += chunk) {
         const int nb = (bs - b0 < chunk) ? bs - b0 : chunk;
         XProd none = {};
-        none.ahead = (flags & QP_FLAG_DECODE_AHEAD) ? 1 : ((flags & QP_FLAG_TABLE_LATE) ? 2 : 0);
-        none.late_ctas = (int)((flags >> 8) & 0xffu);           // QP_FLAG_SKEW(ctas, permille)
-        none.late_permille = (int)((flags >> 16) & 0x3ffu);
         rc = dispatch_gemv(L, S, out + (size_t)b0 * M, (const __half *)x_f16 + (size_t)b0 * K, tlut_f16, M, K, nb, none, st);
         if (rc != QP_OK) return rc;
     }

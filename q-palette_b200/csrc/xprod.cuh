@@ -49,11 +49,6 @@ struct XProd {
     const unsigned *ll_epoch; // epoch the entries must carry (written by the local sender launched in front of this kernel)
     int ll_kind;              // 1: the LL values are fp16(acc) (src is read normally); 2: they are src
     unsigned long long ll_spin_cycles;  // 0 = poll forever
-    // prologue order of the GEMV kernels (also read in mode 0), see tcq_gemv_kernel: 0 table first, 1 decode ahead, 2 table late
-    int ahead;
-    // work split of the GEMV launch (gemv_common.cuh, make_split_skewed): the last late_ctas CTAs get late_permille / 1000 of the
-    // others' share; 0 / 1000 = even split
-    int late_ctas, late_permille;
 };
 
 // LL entries are read at L2 (ld.volatile), where the peers' NVLink stores land; an 8-byte {data, flag} half of an entry is
@@ -149,10 +144,8 @@ __device__ __forceinline__ void xp_preload(XPre<CH> &r, const XProd &p, int n) {
 // CH = ceil(n / 4 / blockDim.x) chunks of 4 consecutive elements per thread.
 // LL (compile time): one operand is polled out of the row-sharded receive buffer (p.ll); a separate instantiation because the
 // polling registers and branches cost the single-GPU prologue 1.3 % of a decode step when they are merely present (measured)
-// `mid` runs once after every load of the dependent inputs has been issued and before the first of them is used (the GEMV
-// kernels fill the shared-memory codebook there, under the L2 round trip)
-template <int CH, bool LL = false, class Mid>
-__device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n, const XPre<CH> &pre, Mid mid) {
+template <int CH, bool LL = false>
+__device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, const XProd &p, int n, const XPre<CH> &pre) {
     const int nch = n >> 2, T = blockDim.x;
     QP_XPHASE(0);
     uint2 hv[CH];
@@ -168,24 +161,13 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
             lv[j] = c < nch ? xp_ll_load(p_ll + c) : make_uint4(0u, ll_ep, 0u, ll_ep);
             if (p.ll_kind != 2) hv[j] = c < nch ? __ldcg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
         }
-    } else {
-        // activations / accumulators are rewritten by other kernels within one decode step and kernels overlap under programmatic
-        // dependent launch: read them at L2 (ld.global.cg), never through the non-coherent L1 path (measured round 2: with
-        // ld.global.nc a CTA could see a stale line of `acc` / `src` and the fused launch list diverged from the un-fused one)
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const int c = threadIdx.x + j * T;
-            const bool ok = c < nch;
-            hv[j] = ok ? __ldcg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
-            av[j] = (ok && p.acc) ? __ldcg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
     }
-    mid();
-    if (p_ll) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const int c = threadIdx.x + j * T;
-            const uint2 g = xp_ll_wait(lv[j], p_ll + (c < nch ? c : 0), ll_ep, p.ll_spin_cycles);
+    for (int j = 0; j < CH; ++j) {
+        const int c = threadIdx.x + j * T;
+        const bool ok = c < nch;
+        if (p_ll) {
+            const uint2 g = xp_ll_wait(lv[j], p_ll + (ok ? c : 0), ll_ep, p.ll_spin_cycles);
             if (p.ll_kind == 2) {
                 hv[j] = g;
                 av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,7 +176,13 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
                 xp_unpack4(g, a4);  // fp16(acc): exactly what the arithmetic below makes of an fp32 accumulator first
                 av[j] = make_float4(a4[0], a4[1], a4[2], a4[3]);
             }
+            continue;
         }
+        // activations / accumulators are rewritten by other kernels within one decode step and kernels overlap under programmatic
+        // dependent launch: read them at L2 (ld.global.cg), never through the non-coherent L1 path (measured round 2: with
+        // ld.global.nc a CTA could see a stale line of `acc` / `src` and the fused launch list diverged from the un-fused one)
+        hv[j] = ok ? __ldcg(reinterpret_cast<const uint2 *>(p.src) + c) : make_uint2(0u, 0u);
+        av[j] = (ok && p.acc) ? __ldcg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     QP_XPHASE(1);  // loads issued, zero slices stored
     const __half hs = __float2half(p.acc_scale);
@@ -283,11 +271,11 @@ __device__ __forceinline__ void produce_x_dispatch(uint32_t *xs, float *v, float
     if (ch <= 2) {
         XPre<2> pre;
         xp_preload<2>(pre, p, n);
-        produce_x<2, LL>(xs, v, red, p, n, pre, [] {});
+        produce_x<2, LL>(xs, v, red, p, n, pre);
     } else {  // host guarantees n <= 5 * 4 * blockDim.x
         XPre<5> pre;
         xp_preload<5>(pre, p, n);
-        produce_x<5, LL>(xs, v, red, p, n, pre, [] {});
+        produce_x<5, LL>(xs, v, red, p, n, pre);
     }
 }
 

@@ -9,13 +9,6 @@ LIB_PATH = os.path.join(_HERE, f"libqpalette{os.environ.get('QP_LIB_SUFFIX', '')
 QP_OK = 0
 SPLIT_NONE, SPLIT_IN, SPLIT_OUT = 0, 1, 2
 FLAG_ACCUMULATE = 1
-FLAG_DECODE_AHEAD = 2  # GEMV prologue orders kept for A/B timing (include/qpalette.h); the default order is the fastest
-FLAG_TABLE_LATE = 4
-
-
-def flag_skew(ctas, permille):
-    """QP_FLAG_SKEW of include/qpalette.h: the last `ctas` CTAs of a GEMV grid get permille / 1000 of the others' share"""
-    return ((ctas & 0xff) << 8) | ((permille & 0x3ff) << 16)
 EPI_NONE, EPI_SILU_MUL = 0, 1
 
 _lib = None
@@ -74,7 +67,7 @@ class XProd(ctypes.Structure):
     _fields_ = [("src_f16", _vp), ("h_out_f16", _vp), ("acc", _vp), ("wscale_f16", _vp), ("acc_scale", _f),
                 ("norm_w_f16", _vp), ("eps", _f), ("su_f16", _vp), ("had_scale", _f), ("x_out_f16", _vp),
                 ("zero1", _vp), ("zero1_count", _i), ("zero2", _vp), ("zero2_count", _i),
-                ("ll", _vp), ("ll_epoch", _vp), ("ll_kind", _i), ("prologue_order", _i), ("late_ctas", _i), ("late_permille", _i)]
+                ("ll", _vp), ("ll_epoch", _vp), ("ll_kind", _i)]
 
 
 class Xchg(ctypes.Structure):

@@ -16,7 +16,6 @@ are all-gathered with NCCL at the four layer boundaries.
 """
 import ctypes
 import math
-import os
 from dataclasses import dataclass, field
 
 import torch
@@ -104,22 +103,18 @@ class _Proj:
         self.weight_bytes = self.codes1.numel() * self.codes1.element_size() + \
             (self.codes2.numel() * self.codes2.element_size() if self.codes2 is not None else 0)
 
-    def launch(self, out_ptr, x_ptr, stream, ahead=0, skew=(0, 0)):
-        """ahead: prologue order of include/qpalette.h (0 default, 1 decode ahead, 2 table late; A/B timing only);
-        skew = (late_ctas, permille): work split of the launch (QP_FLAG_SKEW)"""
+    def launch(self, out_ptr, x_ptr, stream):
         L = lib()
-        sk = _cabi.flag_skew(*skew) if skew[0] else 0
         if self.kind in ("tcq_ldlq", "combt_ldlq"):
-            hint = {0: 0, 1: _cabi.FLAG_DECODE_AHEAD, 2: _cabi.FLAG_TABLE_LATE}[ahead] | sk
             check(L.qp_tcq_gemv(out_ptr, self.codes1.data_ptr(), self.codes2.data_ptr() if self.codes2 is not None else None,
                                 x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.S, self.KV1, self.KV2, self.split,
-                                self.part1, FLAG_ACCUMULATE | hint, stream))
+                                self.part1, FLAG_ACCUMULATE, stream))
         elif self.simt:
             check(L.qp_simt_gemv(out_ptr, self.codes1.data_ptr(), x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.bits,
                                  self.vec, 1, stream))
         else:
             check(L.qp_lut_gemv(out_ptr, self.codes1.data_ptr(), x_ptr, self.lut.data_ptr(), self.M, self.K, 1, self.bits,
-                                self.vec, FLAG_ACCUMULATE | sk, stream))
+                                self.vec, FLAG_ACCUMULATE, stream))
 
 
     def can_fuse(self):
@@ -148,9 +143,6 @@ def silu_grid_supported(I):
 
 
 class DecodeRunner:
-    # default work split of the four GEMV sites of a layer, (late CTAs, permille of the others' share): see _step_fused
-    SKEW = {}
-
     def __init__(self, shape=LLAMA31_8B, qdict=None, merge_info=None, max_seq=512, device="cuda", seed=0, rank=0,
                  world=1, process_group=None, num_layers=None, random_scales=True, fused=True, p2p=True):
         """world > 1: rows of every projection are sharded over the ranks of `process_group`.  p2p=True gathers
@@ -411,27 +403,6 @@ class DecodeRunner:
                 if i != lead:
                     proj.launch(p(acc_buf) + 4 * off, p(x_buf), st)
 
-        # GEMV prologue orders (include/qpalette.h, qp_xprod.prologue_order), for A/B timing only: QP_AHEAD_MODE = late | ahead |
-        # mixed (qkv / ug, which follow a GEMV: late; o / down, which follow a short kernel: decode ahead).  The default order
-        # (codebook fill before the dependency wait) measured fastest: profiles/r02_prologue_orders.log
-        mode = os.environ.get("QP_AHEAD_MODE", "old")
-        after_gemv, after_glue = {"mixed": (2, 1), "old": (0, 0), "late": (2, 2), "ahead": (1, 1)}[mode]
-        # work split per call site (qp_xprod.late_ctas / late_permille): CTAs are dispatched in index order, so the LAST CTAs of a
-        # GEMV grid start late when the preceding kernel still holds their SMs (attention, the SiLU cluster, another GEMV's
-        # slowest CTAs) and the launch ends with them; they get a smaller share.  Measured per site with
-        # tools/phase_profile_step.py; QP_SKEW="qkv:ctas:permille,o:..,ug:..,down:.." overrides, QP_SKEW=off = even split
-        skew = dict(self.SKEW)
-        env = os.environ.get("QP_SKEW", "")
-        if env == "off":
-            skew = {}
-        elif env:
-            for item in env.split(","):
-                k, c, pm = item.split(":")
-                skew[k] = (int(c), int(pm))
-
-        def with_skew(prod, site):
-            prod.late_ctas, prod.late_permille = skew.get(site, (0, 0))
-            return prod
         prev = None
         for ly in self.layers:
             if prev is None:
@@ -439,8 +410,7 @@ class DecodeRunner:
             else:
                 prod = xp(hc, h_out=ho, acc=self.acc_dn, ws=prev["W_dp_full"], norm=ly["norm1"], su=ly["SU_qkv"],
                           z1=self.acc_o, z2=self.acc_ug)
-            prod.prologue_order = after_gemv
-            run_group(ly["qkv"], self.acc_qkv, with_skew(prod, "qkv"), self.x_h)
+            run_group(ly["qkv"], self.acc_qkv, prod, self.x_h)
             if prev is not None:
                 hc, ho = ho, hc
             check(L.qp_rope_attention(p(self.attn), p(self.acc_qkv), p(ly["W_qkv"]), S, p(self.inv_freq), p(ly["kc"]),
@@ -449,18 +419,16 @@ class DecodeRunner:
             # fused launches clear accumulators BEFORE their dependency wait: only buffers the preceding launch does not
             # touch (the attention kernel still reads acc_qkv while the o projection starts, so ug clears it instead)
             prod = xp(self.attn, su=ly["SU_o"], z2=self.acc_dn)
-            prod.prologue_order = after_glue
-            run_group([(ly["o"], 0)], self.acc_o, with_skew(prod, "o"), self.x_h)
+            run_group([(ly["o"], 0)], self.acc_o, prod, self.x_h)
             prod = xp(hc, h_out=ho, acc=self.acc_o, ws=ly["W_o_full"], norm=ly["norm2"], su=ly["SU_ug"], z1=self.acc_qkv)
-            prod.prologue_order = after_gemv
-            run_group(ly["ug"], self.acc_ug, with_skew(prod, "ug"), self.x_h)
+            run_group(ly["ug"], self.acc_ug, prod, self.x_h)
             hc, ho = ho, hc
             if self.silu_grid:  # one thread-block cluster, blocks exchanged through distributed shared memory
                 check(L.qp_silu_mul_had_cluster(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0,
                                                 st))
             else:
                 check(L.qp_silu_mul_had(p(self.x_i), p(self.acc_ug), p(ly["W_ug"]), S, p(ly["SU_dp"]), I, s_i, None, 0, st))
-            ly["down"].launch(p(self.acc_dn), p(self.x_i), st, ahead=after_glue, skew=skew.get("down", (0, 0)))
+            ly["down"].launch(p(self.acc_dn), p(self.x_i), st)
             prev = ly
         check(L.qp_fused_norm_had(p(self.xf), p(hc), 1, p(self.acc_dn), p(prev["W_dp_full"]), S, p(self.final_norm),
                                   sh.rms_norm_eps, None, H, 1.0, 0, None, 0, st))

@@ -47,20 +47,3 @@ def test_lut_code_extraction(emul, vec, R):
         f = O._matrix_to_frag(codes)
         frag = f[..., 0] | (f[..., 1] << R)
     assert np.array_equal(out.reshape(frag.shape), frag)
-
-
-@pytest.mark.parametrize("T", [0, 1, 5, 147, 148, 3551, 3552, 3553, 16384, 24576, 28672, 57344, 114688, 1000003])
-def test_run_split_tiles_the_range(emul, T):
-    """csrc/run_split.cuh: every (even, flipped or skewed) two-level split of T super-tiles over 148 CTAs x 24 warps tiles [0, T)
-    in (CTA, warp) order, the CTAs of a class carry the same load +-1, no warp more than its CTA's share / 24 rounded up, and a
-    skewed split gives the last CTAs the requested smaller share"""
-    lo_, hi_, late_, wm = (ctypes.c_uint(0) for _ in range(4))
-    for flip in (0, 1):
-        for late, pm in ((0, 0), (7, 890), (19, 900), (10, 960), (147, 500), (1, 0), (148, 900), (7, 1000), (30, 10)):
-            rc = emul.qp_emul_split_cover(ctypes.c_long(T), 148, 24, late, pm, flip, ctypes.byref(lo_), ctypes.byref(hi_),
-                                          ctypes.byref(late_), ctypes.byref(wm))
-            assert rc == 0, (late, pm, flip)
-            assert hi_.value - lo_.value <= 1, (late, pm, flip)
-            assert wm.value <= -(-max(hi_.value, late_.value) // 24), (late, pm, flip)
-            if 0 < late < 148 and pm < 1000 and T >= 57344:
-                assert abs(late_.value / max(hi_.value, 1) - pm / 1000) < 0.02, (late, pm, hi_.value, late_.value)

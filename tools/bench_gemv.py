@@ -59,13 +59,10 @@ def tcq_case(M, K, kv, S=9, bs=1, graph=True):
             bufs.append((torch.randint(0, 256, (nb,), dtype=torch.uint8, device=dev), None))
     out = torch.zeros((bs, M), dtype=torch.float32, device=dev)
 
-    hint = int(os.environ.get("QP_GEMV_HINT", "0"))  # prologue-order flags of include/qpalette.h: 2 = decode ahead, 4 = table late
-
     def mk(b):
         if two:
-            return lambda: ops.tcq_gemv(b[0], x, tl, M, K, S, kv[0], b[1], kv[1], SPLIT_IN, K // 2, out=out, accumulate=True,
-                                        hint=hint)
-        return lambda: ops.tcq_gemv(b[0], x, tl, M, K, S, kv, out=out, accumulate=True, hint=hint)
+            return lambda: ops.tcq_gemv(b[0], x, tl, M, K, S, kv[0], b[1], kv[1], SPLIT_IN, K // 2, out=out, accumulate=True)
+        return lambda: ops.tcq_gemv(b[0], x, tl, M, K, S, kv, out=out, accumulate=True)
 
     fns = [mk(b) for b in bufs]
     alg = nb + 2 * bs * K + 4 * bs * M + (1 << S) * 4
