@@ -13,6 +13,6 @@ ncu --graph-profiling node --metrics gpu__time_duration.sum,dram__bytes_read.sum
     python tools/bench_gemv.py --one tcq:4096:14336:6,7 --iters 60 > gpurun_out/r2f_ncu_graph.log 2>&1
 # (3) launch list of the bench command
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-tp-extra > gpurun_out/r2f_bench_short.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2f_launches_bench.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:tcq_|lut_|silu_mul|rope_attention|gemv_f16|embed_kernel|argmax_kernel|fused_norm_had|step_advance" -c 420 --csv --log-file gpurun_out/r2f_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-tp-extra > gpurun_out/r2f_ncu_launches.log 2>&1
 ls -la gpurun_out | tail -8
