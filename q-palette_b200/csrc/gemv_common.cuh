@@ -228,6 +228,9 @@ __device__ __forceinline__ void dequant_run_segment(const PackSegment seg, __hal
 #ifndef QP_REFILL_LATE
 #define QP_REFILL_LATE 1
 #endif
+#ifndef QP_TRIP_CHECK
+#define QP_TRIP_CHECK 0  // measured: 18.84 -> 18.56 us at 28672x4096 but 6.15 -> 6.26 at 6144x4096, decode step 498.3 vs 503.5 tok/s (profiles/r02_loop_variants.log)
+#endif
 constexpr int kGemv2Depth = QP_GEMV2_DEPTH;
 
 struct WarpRun2 {
@@ -349,6 +352,23 @@ __device__ __forceinline__ void gemv2_run(const PackSegment seg, float *__restri
     };
     // main loop: D valid steps per trip; a refill is predicated on its super-tile being inside the run
     for (; i + D <= n; i += D) {
+#if QP_TRIP_CHECK
+        // the strip end is tested once per trip: a trip that stays inside the strip runs D steps as ONE basic block (no countdown,
+        // compare and branch per step, and ptxas may overlap a step's lookups with the next step's extraction)
+        if (kleft > D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                uint32_t P[G::kWords];
+                tcq_align<E>(raw[d], bitoff, P);
+                gemv2_consume<Dec>(P, xa, lane, tab_lane, acc);
+                pack_load_raw_pred<E>(raw[d], p + d * SBw, i + d + D < n);
+                xa += xstep;
+            }
+            kleft -= D;
+            p += D * SBw;
+            continue;
+        }
+#endif
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             uint32_t P[G::kWords];
