@@ -105,7 +105,13 @@ struct PackSegment {
     int ksuper;             // cols / 32
     int row0;               // first output row
     int ksuper0;            // first super-tile column of x
+    unsigned kmagic = 0;    // floor(2^32 / ksuper), set by the GEMV launchers (seg_with_magic): strip / column of a flat index
+                            // without the ~30-instruction division sequence on the path between "x staged" and the loop
 };
+inline PackSegment seg_with_magic(PackSegment s) {
+    s.kmagic = s.ksuper <= 1 ? 0xffffffffu : (unsigned)((1ull << 32) / (unsigned)s.ksuper);
+    return s;
+}
 
 #ifndef QP_GEMV_THREADS
 #define QP_GEMV_THREADS 768
@@ -244,8 +250,14 @@ __device__ __forceinline__ WarpRun2 warp_run2(const PackSegment seg, const RunSp
     WarpRun2 r;
     r.lo = lo;
     r.n = (int)(hi - lo);
-    r.mh = (int)(lo / (unsigned)seg.ksuper);
-    r.kh = (int)(lo - (unsigned)r.mh * (unsigned)seg.ksuper);
+    // lo / ksuper by multiplication: q = hi32(lo * floor(2^32 / ksuper)) is the quotient or one less (lo < 2^32)
+    unsigned q = __umulhi(lo, seg.kmagic), rem = lo - q * (unsigned)seg.ksuper;
+    if (rem >= (unsigned)seg.ksuper) {
+        q += 1u;
+        rem -= (unsigned)seg.ksuper;
+    }
+    r.mh = (int)q;
+    r.kh = (int)rem;
     return r;
 }
 

@@ -177,7 +177,7 @@ static int launch_lut_gemv(PackSegment seg, float *out, const void *x, const voi
     const size_t smem = (size_t)T::kBytes + 4 * (size_t)lut_compact_words(E, r_single) + (size_t)K * bs * 2 +
                         (prod.mode ? (size_t)K * 4 : 0);
     QP_CHECK_ARG(smem <= (size_t)kMaxSmem - 256, "K = %d does not fit the fused-prologue shared-memory budget", K);
-    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg,
+    QP_CUDA(launch_pdl(kern, dim3(sm_count()), dim3(kGemvThreads), smem, st, seg_with_magic(seg),
                        make_split((long)seg.strips * seg.ksuper, sm_count() * kGemvWarps), out, (const uint32_t *)x, lut,
                        r_single, M, K, bs, prod));
     return check_launch("lut_gemv");

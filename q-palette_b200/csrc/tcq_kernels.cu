@@ -351,7 +351,7 @@ static int launch_gemv(const TcqLaunch &L, float *out, const void *x, const void
     }
     const int nctas = sm_count() * kGemvCtasPerSM;
     const int nwarps = nctas * kTcqWarps;
-    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, L.a, L.b,
+    QP_CUDA(launch_pdl(kern, dim3(nctas), dim3(kTcqThreads), smem, st, seg_with_magic(L.a), seg_with_magic(L.b),
                        make_split((long)L.a.strips * L.a.ksuper, nwarps), make_split((long)L.b.strips * L.b.ksuper, nwarps),
                        out, (const uint32_t *)x, (const uint32_t *)tlut, M, K, bs, prod));
     return check_launch("tcq_gemv");
