@@ -88,11 +88,13 @@ __device__ __forceinline__ void had_warp128(float (&y)[4]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
-        const bool upper = (lane >> s) & 1;
+        // o - y for the upper lane of a pair, y + o for the lower one, as ONE fused multiply-add by +-1 (bit-identical; the
+        // select form costs two adds and a select per element and stage, and this runs in every CTA of a fused launch)
+        const float sgn = ((lane >> s) & 1) ? -1.f : 1.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float o = __shfl_xor_sync(0xffffffffu, y[e], 1 << s);
-            y[e] = upper ? (o - y[e]) : (y[e] + o);
+            y[e] = fmaf(y[e], sgn, o);
         }
     }
 }

@@ -79,5 +79,26 @@ print(f"{'M':>6} {'K':>6} ah ctas | start min/med/max      | prework med | wait 
 for rw in rows[-4 * min(layers, 3) - 1:]:
     print(f"{rw[0]:6d} {rw[1]:6d} {rw[2]:2d} {rw[3]:4d} | {rw[4]:6d} {rw[5]:6d} {rw[6]:6d} | {rw[7]:8d} | {rw[8]:7d} {rw[9]:7d} | {rw[10]:7d} {rw[11]:7d} | "
           f"{rw[12]:7d} {rw[13]:7d} | {rw[14]:6d}")
+# sub-phases of the fused x-producer prologue: g_xphase holds the LAST fused launch of the step (the last layer's up/gate GEMV)
+try:
+    xb = np.zeros((256, 8), dtype=np.uint64)
+    L.qp_debug_xphases.argtypes = [ctypes.c_void_p]
+    L.qp_debug_xphases(xb.ctypes.data_as(ctypes.c_void_p))
+    xb = xb[:148, :6].astype(np.int64)
+    xmode = (rec[:, 1] >> 16) & 3
+    fused = [(a, b) for (a, b) in groups if xmode[a] == 1]
+    a, b = fused[-1]
+    cta = rec[a:b, 1] & 0xFFFF
+    wait_done = np.zeros(148, dtype=np.int64)
+    wait_done[cta] = t[a:b, 3]
+    staged = np.zeros(148, dtype=np.int64)
+    staged[cta] = t[a:b, 4]
+    relx = xb - wait_done[:, None]
+    print(f"x-producer sub-phases of the last fused launch ({int(M[a])}x{int(K[a])}), ns after the CTA's dependency wait, median / max over CTAs:")
+    for i, nm in enumerate(["enter", "loads issued", "inputs arrived, residual added", "normalised", "in-warp stages done, in smem", "hadamard done"]):
+        print(f"    {nm:32s} {int(np.median(relx[:, i])):6d} / {int(relx[:, i].max()):6d}")
+    print(f"    {'x staged (fragment order, barrier)':32s} {int(np.median(staged - wait_done)):6d} / {int((staged - wait_done).max()):6d}")
+except Exception as e:  # noqa: BLE001
+    print("x-phase stamps unavailable:", e)
 per_layer = (t[:, 6].max() - t0) / max(1, layers)
 print(f"span of all GEMV launches of the step: {(t[:, 6].max() - t0) / 1e3:.1f} us = {per_layer / 1e3:.1f} us / layer")
