@@ -96,7 +96,9 @@ int qp_lut_gemm_tc(float *out, const void *codes, const void *x_f16, const void 
  * VQ / SQ in the SIMT layout (lib/quantizer/pack_op.py:288-335, quant_op.py:33-86).  out: fp16 (bs, M).
  * Replaces sq_pack_gemm.pack_gemm / pack_dequant (kernels/sq-cuda-kernels/gemm_routines.cu:474-722) and
  * vq_pack_gemm.vq_pack_gemm_* / vq_pack_dequant_* (kernels/vq-cuda-kernels/src/gemm_routines.cu:1913-2120).
- * Accumulates in fp32 (the reference accumulates in fp16).
+ * Accumulates in fp32 (the reference accumulates in fp16).  vec_sz 1 (SQ, 2..8 bits), 2 (3..12 bits; 2 accepted) and
+ * 4 (6..12 bits): the op table of lib/linear/__init__.py:339-420.  K % (32*vec_sz) == 0; a last chunk shorter than
+ * 32*32*vec_sz weights is packed with the reduced thread count the reference packer uses (quant_op.py:15-31).
  * ------------------------------------------------------------------------------------------------------------- */
 int qp_simt_gemv(void *out, const void *codes, const void *x_f16, const void *lut_f16, int M, int K, int bs,
                  int bits, int vec_sz, int out_is_f32 /* 0: fp16 (bs,M) like the reference op; 1: fp32 */, void *stream);

@@ -1,5 +1,5 @@
 // simt_kernels.cu -- LUT GEMV / dequantise for Q-Palette's SIMT packed layouts (lib/quantizer/pack_op.py:288-335 for
-// vec_sz 1, lib/quantizer/quant_op.py:33-78 for vec_sz 2) and the tensor-core -> SIMT format conversion
+// vec_sz 1, lib/quantizer/quant_op.py:33-78 for vec_sz 2 and 4) and the tensor-core -> SIMT format conversion
 // (lib/quantizer/quant_op.py:246-257).  Replaces kernels/sq-cuda-kernels/gemm_routines.cu:474-722 and
 // kernels/vq-cuda-kernels/src/gemm_routines.cu:1913-2120.
 //
@@ -23,17 +23,21 @@ struct SimtTable {
     static constexpr int kFieldBits = kPair ? 2 * BITS : BITS;
     static constexpr int kSL = (kFieldBits <= 10) ? 7 : (17 - kFieldBits);
     static constexpr int kBytes = (1 << kFieldBits) << kSL;
-    static constexpr uint32_t kLaneMask = (1u << (kSL - 2)) - 1u;
+    // VEC = 4: an entry is four fp16 = 8 bytes, read with one LDS.64; a 64-bit shared load is served per half-warp, so 16
+    // copies (one 128-byte slot) are already conflict-free
+    static constexpr int kEntryShift = (VEC == 4) ? 3 : 2;
+    static constexpr uint32_t kLaneMask = (1u << (kSL - kEntryShift)) - 1u;
 };
 
 template <int BITS, int VEC>
 __device__ __forceinline__ void simt_build_table(uint32_t *tab, const uint32_t *lc) {
     using T = SimtTable<BITS, VEC>;
-    constexpr int copies = 1 << (T::kSL - 2);
+    constexpr int copies = 1 << (T::kSL - T::kEntryShift);
     const uint16_t *l16 = reinterpret_cast<const uint16_t *>(lc);
     for (int i = threadIdx.x; i < (1 << T::kFieldBits) * copies; i += blockDim.x) {
         const int e = i / copies;
-        if (VEC == 2) tab[i] = lc[e];
+        if (VEC == 4) reinterpret_cast<uint2 *>(tab)[i] = reinterpret_cast<const uint2 *>(lc)[e];
+        else if (VEC == 2) tab[i] = lc[e];
         else if (T::kPair) tab[i] = (uint32_t)l16[e & ((1 << BITS) - 1)] | ((uint32_t)l16[e >> BITS] << 16);
         else tab[i] = (uint32_t)l16[e];
     }
@@ -58,7 +62,11 @@ template <int BITS, int VEC, int G>
 __device__ __forceinline__ void simt_group(const uint32_t (&w)[BITS], uint32_t tab, uint32_t (&h)[4]) {
     using T = SimtTable<BITS, VEC>;
     constexpr int SL = T::kSL, FB = T::kFieldBits;
-    if constexpr (VEC == 2 || T::kPair) {  // one lookup per fp16 pair
+    if constexpr (VEC == 4) {  // one 64-bit lookup per four weights
+        const uint2 a = *reinterpret_cast<const uint2 *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 2 + 0, SL>(w) | tab));
+        const uint2 b = *reinterpret_cast<const uint2 *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 2 + 1, SL>(w) | tab));
+        h[0] = a.x, h[1] = a.y, h[2] = b.x, h[3] = b.y;
+    } else if constexpr (VEC == 2 || T::kPair) {  // one lookup per fp16 pair
         h[0] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 0, SL>(w) | tab));
         h[1] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 1, SL>(w) | tab));
         h[2] = *reinterpret_cast<const uint32_t *>(qp_dyn_smem + (simt_code_offset<BITS, FB, G * 4 + 2, SL>(w) | tab));
@@ -141,7 +149,7 @@ simt_kernel(__half *__restrict__ out, const uint32_t *__restrict__ codes, const 
     if (GEMV) coop_copy_words<true>(xs, reinterpret_cast<const uint32_t *>(x), bs * K / 2);
     __syncthreads();
     pdl_launch_dependents();
-    const uint32_t tab_lane = (lane & T::kLaneMask) << 2;  // lane column; the table starts the dynamic shared memory (qp_dyn_smem)
+    const uint32_t tab_lane = (lane & T::kLaneMask) << T::kEntryShift;  // lane column; the table starts the dynamic shared memory (qp_dyn_smem)
     const uint32_t xs_addr = smem_u32(xs);
     const int row_words = BITS * K / 32 / VEC;
     const int nfull = K / kChunk, rem = K % kChunk;
@@ -228,6 +236,8 @@ static int dispatch_simt(int bits, int vec_sz, __half *out, const void *codes, c
     QP_C(2, 1) QP_C(3, 1) QP_C(4, 1) QP_C(5, 1) QP_C(6, 1) QP_C(7, 1) QP_C(8, 1)
     QP_C(2, 2) QP_C(3, 2) QP_C(4, 2) QP_C(5, 2) QP_C(6, 2) QP_C(7, 2) QP_C(8, 2) QP_C(9, 2) QP_C(10, 2) QP_C(11, 2)
     QP_C(12, 2)
+    // ours_lib::vq_pack_{gemm,dequant}_simt_*_4_{6..12} (lib/linear/__init__.py:383-420)
+    QP_C(6, 4) QP_C(7, 4) QP_C(8, 4) QP_C(9, 4) QP_C(10, 4) QP_C(11, 4) QP_C(12, 4)
 #undef QP_C
     return fail(QP_ERR_ARG, "unsupported SIMT configuration bits=%d vec_sz=%d", bits, vec_sz);
 }
@@ -287,7 +297,7 @@ using namespace qp;
 
 static int simt_check(const void *codes, int M, int K, int bits, int vec_sz) {
     QP_CHECK_ARG(codes != nullptr, "codes is NULL");
-    QP_CHECK_ARG(vec_sz == 1 || vec_sz == 2, "SIMT layout: vec_sz 1 or 2 supported (got %d)", vec_sz);
+    QP_CHECK_ARG(vec_sz == 1 || vec_sz == 2 || vec_sz == 4, "SIMT layout: vec_sz 1, 2 or 4 supported (got %d)", vec_sz);
     QP_CHECK_ARG(M > 0 && K > 0 && K % (32 * vec_sz) == 0, "SIMT layout needs K %% (32*vec_sz) == 0 (K=%d)", K);
     return check_align(codes, 4, "codes");
 }

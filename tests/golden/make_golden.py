@@ -140,6 +140,17 @@ def main():
         flat += list(kv) if isinstance(kv, list) else [kv, -1]
         out[f"qinfo_{qs}"] = np.array(flat, dtype=np.int64)
 
+    # ---- SIMT layout with 4-wide vectors (ours_lib::vq_pack_*_simt_*_4_*, lib/linear/__init__.py:383-420); its own generator
+    # so that the arrays above keep their values
+    rng4 = np.random.default_rng(404)
+    for R in (6, 8, 10, 12):
+        for K in (4096, 4096 + 1024):
+            M = 8
+            Q = torch.from_numpy(rng4.integers(0, 1 << R, size=(M, K // 4), dtype=np.int64))
+            packed = quant_op.pack_qweight_vq_simt(Q, R, 4, R)
+            out[f"simt_codes_4_{R}_{K}"] = Q.numpy().astype(np.int32)
+            out[f"simt_packed_4_{R}_{K}"] = packed.numpy().view(np.int32).reshape(M, -1)
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 

@@ -178,7 +178,8 @@ def test_lut_tc(ops, golden, vec, R):
 
 # --------------------------------------------------------------------------------------------------------- SIMT layout
 SIMT_CASES = [(1, r, k) for r in (2, 3, 4, 5, 6, 7, 8) for k in (1024, 1280)] + \
-             [(2, r, k) for r in (2, 3, 5, 6, 8, 9, 10, 12) for k in (2048, 2560)]
+             [(2, r, k) for r in (2, 3, 5, 6, 8, 9, 10, 12) for k in (2048, 2560)] + \
+             [(4, r, k) for r in (6, 7, 8, 9, 10, 11, 12) for k in (4096, 5120)]  # 4-wide vectors: lib/linear/__init__.py:383-420
 
 
 @pytest.mark.parametrize("vec,R,K", SIMT_CASES)
@@ -281,3 +282,17 @@ def test_reference_operator_names(ops):
         assert tuple(fy.shape) == (1, M) and fy.dtype == torch.float32
     with pytest.raises(AttributeError):
         ops.resolve("decompress_gemm_tcq_not_an_op")
+    # SIMT ops with 4-wide vectors exist for 6..12-bit codes, as in the reference (lib/linear/__init__.py:383-420)
+    R4, K4, M4 = 8, 4096, 64
+    lut4 = rng.standard_normal((1 << R4, 4)).astype(np.float16)
+    codes4 = rng.integers(0, 1 << R4, size=(M4, K4 // 4))
+    packed4 = cuda(O.simt_pack(codes4, M4, K4, R4, 4))
+    x4 = cuda(rng.standard_normal((2, 1, K4)).astype(np.float16))
+    y4 = ops.resolve(f"vq_pack_gemm_simt_2_4_{R4}")(x4, packed4, cuda(lut4))
+    assert tuple(y4.shape) == (2, 1, M4) and y4.dtype == torch.float16
+    W4 = ops.resolve(f"vq_pack_dequant_simt_4_{R4}")(packed4, cuda(lut4), M4, K4)
+    assert bits_equal(W4, lut4[codes4].reshape(M4, K4))
+    assert rel_l2(y4.cpu().numpy().reshape(2, M4), O.gemv_ref(lut4[codes4].reshape(M4, K4), x4.cpu().numpy().reshape(2, K4))) <= 2e-3
+    for bad in ("vq_pack_gemm_simt_1_4_5", "vq_pack_dequant_simt_4_13", "vq_pack_dequant_simt_3_8"):
+        with pytest.raises(AttributeError):
+            ops.resolve(bad)

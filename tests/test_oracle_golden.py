@@ -73,7 +73,8 @@ def test_lut_tc_layout(golden, vec, R):
 
 
 @pytest.mark.parametrize("vec,R,K", [(1, r, k) for r in (2, 3, 4, 5, 8) for k in (1024, 1280)] +
-                         [(2, r, k) for r in (3, 6, 8, 12) for k in (2048, 2560)])
+                         [(2, r, k) for r in (3, 6, 8, 12) for k in (2048, 2560)] +
+                         [(4, r, k) for r in (6, 8, 10, 12) for k in (4096, 5120)])
 def test_simt_layout(golden, vec, R, K):
     Q = golden[f"simt_codes_{vec}_{R}_{K}"]
     packed = golden[f"simt_packed_{vec}_{R}_{K}"]

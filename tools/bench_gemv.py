@@ -125,7 +125,7 @@ def main():
                 cases.append(("lut", shape, (bits, vec)))
     if a.cases in ("simt", "all"):
         for shape in ((4096, 14336), (14336, 4096)):
-            for vec, bits in ((2, 6), (2, 8), (2, 10), (1, 4), (1, 6)):
+            for vec, bits in ((2, 6), (2, 8), (2, 10), (1, 4), (1, 6), (4, 8), (4, 10), (4, 12)):
                 cases.append(("simt", shape, (bits, vec)))
     if a.one:
         kind, M, K, p = a.one.split(":")
