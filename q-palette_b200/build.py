@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v"]
 # tuning knobs of the streaming GEMV kernels (see csrc/gemv_common.cuh); override for experiments
-for _k in ("QP_GEMV_THREADS", "QP_PROFILE_PHASES", "QP_HASH_ADD", "QP_TC_TCQ_STRIDE", "QP_GEMV_CTAS", "QP_TCQ_FOLD", "QP_TC_BACKOFF", "QP_TCQ_STRIDE9", "QP_GEMV2_DEPTH", "QP_FAST_BUILD", "QP_MMA_DEPTH4", "QP_MMA_THREADS4", "QP_REFILL_LATE", "QP_TRIP_CHECK"):
+for _k in ("QP_GEMV_THREADS", "QP_PROFILE_PHASES", "QP_HASH_ADD", "QP_TC_TCQ_STRIDE", "QP_GEMV_CTAS", "QP_TCQ_FOLD", "QP_TC_BACKOFF", "QP_TCQ_STRIDE9", "QP_GEMV2_DEPTH", "QP_FAST_BUILD", "QP_MMA_DEPTH4", "QP_MMA_THREADS4", "QP_REFILL_LATE", "QP_TRIP_CHECK", "QP_XP_FINAL32"):
     if os.environ.get(_k):
         FLAGS.append(f"-D{_k}={os.environ[_k]}")
 if os.environ.get("QP_FAST_MATH"):  # experiment: what --use_fast_math does to SiLU / RMSNorm / softmax

@@ -103,6 +103,52 @@ __device__ __forceinline__ void xp_had_warp128(float (&y)[4]) {
     }
 }
 
+#ifndef QP_XP_FINAL32
+#define QP_XP_FINAL32 1
+#endif
+// strides 2^lh ... of a power-of-two n = p.m done in registers down to the last five, which one radix-32 pass finishes; its
+// outputs are scaled, rounded to fp16 and stored in the B-fragment order of stage_x(): element i = 32*kh + pp lands in half
+// ((kh*16 + q*4 + kl*2 + b) << 1) | e with kl = pp >> 4, b = (pp >> 3) & 1, q = (pp >> 1) & 3, e = pp & 1 -- a permutation inside
+// each block of 32, so a thread's 32 results (stride >= 128 apart) share the in-block position.  No trailing barrier.
+__device__ __forceinline__ void xp_final32_stage(float *v, uint32_t *xs, int n, int lh, const XProd &p) {
+    const int lm = 31 - __clz(n);
+    while (lm - lh > 5) {  // n > 4096: bring the remaining strides down to five
+        if (lm - lh >= 8) fwht_pass<3>(v, n, lh), lh += 3;
+        else if (lm - lh == 7) fwht_pass<2>(v, n, lh), lh += 2;
+        else fwht_pass<1>(v, n, lh), lh += 1;
+        __syncthreads();
+    }
+    __half *xh = reinterpret_cast<__half *>(xs);
+    __half *xo = (p.x_out && blockIdx.x == 0) ? p.x_out : nullptr;
+    const int h = 1 << lh;
+    for (int idx = threadIdx.x; idx < (n >> 5); idx += blockDim.x) {
+        const int low = idx & (h - 1), hi = idx >> lh;
+        const int i0 = (hi << (5 + lh)) | low;
+        float r[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = v[i0 + (k << lh)];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if ((k & s) == 0) {
+                    const float a = r[k], b = r[k | s];
+                    r[k] = a + b;
+                    r[k | s] = a - b;
+                }
+            }
+        }
+        const int pp = i0 & 31;
+        const int d0 = ((((i0 >> 5) << 4) + (((pp >> 1) & 3) << 2) + ((pp >> 4) << 1) + ((pp >> 3) & 1)) << 1) | (pp & 1);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const __half o = __float2half_rn(r[k] * p.had_scale);
+            xh[d0 + (k << lh)] = o;
+            if (xo) xo[i0 + (k << lh)] = o;
+        }
+    }
+}
+
 __device__ __forceinline__ void xp_zero_slice(float *p, int count) {
     if (!p) return;
     float4 *p4 = reinterpret_cast<float4 *>(p);
@@ -239,6 +285,16 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
     }
     __syncthreads();
     QP_XPHASE(4);  // strides < 128 done, in shared memory
+#if QP_XP_FINAL32
+    if (p.Kf == 1 && p.m >= 4096) {
+        // power-of-two n >= 4096 (every fused launch of the Llama shapes): the last five strides as ONE radix-32 pass whose
+        // results go straight into the fragment-ordered fp16 stage -- two barriers and two shared-memory round trips fewer than
+        // radix-8 + radix-4 passes followed by a separate staging pass.  Same butterflies in the same order: bit-identical.
+        xp_final32_stage(v, xs, n, 7, p);
+        QP_XPHASE(5);
+        return;  // the caller's barrier publishes xs
+    }
+#endif
     hadamard_smem(v, n, p.m, p.Kf, 7);
     QP_XPHASE(5);  // Hadamard done
     // fp16 x in B-fragment order: element i = 32*kh + 16*kl + 8*b + 2*q + e  ->  word ((kh*4 + q)*4 + kl*2 + b), half e
