@@ -232,29 +232,37 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
         av[j] = (ok && p.acc) ? __ldcg(reinterpret_cast<const float4 *>(p.acc) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     QP_XPHASE(1);  // loads issued, zero slices stored
-    const __half hs = __float2half(p.acc_scale);
+    // fp16 arithmetic on packed pairs (the rounding points of the reference's fp16 tensors: product by the row scale, by the
+    // shared scale, residual add -- each rounded separately, never contracted into an fma).  Chunks past the end (the last of a
+    // warp's CH chunks when n / 4 is not a multiple of the CTA size) are skipped warp-uniformly: the prologue runs in all 24
+    // warps of all CTAs and is issue-bound like the loop behind it.
+    const __half2 hs2 = __float2half2_rn(p.acc_scale);
     float y[CH][4];
     float ss = 0.f;
+    const int wbase = (int)(threadIdx.x & ~31u);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
-        xp_unpack4(hv[j], y[j]);
-        if (p.acc || p.ll_kind == 1) {
-            float w4[4];
-            xp_unpack4(wv[j], w4);
-            const float a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+        if (wbase + j * T >= nch) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const __half t = __hmul(__hmul(__float2half(a4[e]), __float2half(w4[e])), hs);
-                y[j][e] = __half2float(__hadd(__float2half(y[j][e]), t));
-            }
+            for (int e = 0; e < 4; ++e) y[j][e] = 0.f;
+            continue;
+        }
+        __half2 h01 = *reinterpret_cast<const __half2 *>(&hv[j].x), h23 = *reinterpret_cast<const __half2 *>(&hv[j].y);
+        if (p.acc || p.ll_kind == 1) {
+            const __half2 w01 = *reinterpret_cast<const __half2 *>(&wv[j].x), w23 = *reinterpret_cast<const __half2 *>(&wv[j].y);
+            const __half2 a01 = __floats2half2_rn(av[j].x, av[j].y), a23 = __floats2half2_rn(av[j].z, av[j].w);
+            h01 = __hadd2_rn(h01, __hmul2_rn(__hmul2_rn(a01, w01), hs2));
+            h23 = __hadd2_rn(h23, __hmul2_rn(__hmul2_rn(a23, w23), hs2));
             if (p.h_out && blockIdx.x == 0 && c < nch) {
                 uint2 u;
-                *reinterpret_cast<__half2 *>(&u.x) = __floats2half2_rn(y[j][0], y[j][1]);
-                *reinterpret_cast<__half2 *>(&u.y) = __floats2half2_rn(y[j][2], y[j][3]);
+                u.x = *reinterpret_cast<const uint32_t *>(&h01);
+                u.y = *reinterpret_cast<const uint32_t *>(&h23);
                 reinterpret_cast<uint2 *>(p.h_out)[c] = u;
             }
         }
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        y[j][0] = f01.x; y[j][1] = f01.y; y[j][2] = f23.x; y[j][3] = f23.y;
 #pragma unroll
         for (int e = 0; e < 4; ++e) ss += y[j][e] * y[j][e];
     }
@@ -263,17 +271,18 @@ __device__ __forceinline__ void produce_x(uint32_t *xs, float *v, float *red, co
         const float rstd = rsqrtf(xp_block_sum(ss, red) / (float)n + p.eps);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            float w4[4];
-            xp_unpack4(nv[j], w4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                y[j][e] = __half2float(__hmul(__float2half(w4[e]), __float2half(y[j][e] * rstd)));
+            if (wbase + j * T >= nch) continue;
+            const __half2 n01 = *reinterpret_cast<const __half2 *>(&nv[j].x), n23 = *reinterpret_cast<const __half2 *>(&nv[j].y);
+            const float2 f01 = __half22float2(__hmul2_rn(n01, __floats2half2_rn(y[j][0] * rstd, y[j][1] * rstd)));
+            const float2 f23 = __half22float2(__hmul2_rn(n23, __floats2half2_rn(y[j][2] * rstd, y[j][3] * rstd)));
+            y[j][0] = f01.x; y[j][1] = f01.y; y[j][2] = f23.x; y[j][3] = f23.y;
         }
     }
     QP_XPHASE(3);  // normalised
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int c = threadIdx.x + j * T;
+        if (wbase + j * T >= nch) continue;
         if (p.su) {
             float s4[4];
             xp_unpack4(sv[j], s4);

@@ -1,6 +1,6 @@
-for rep in 1 2 3; do for sfx in "" "_old"; do
+for rep in 1 2 3; do for sfx in "" "_f32" "_old"; do
 QP_LIB_SUFFIX=$sfx timeout 300 python bench.py --no-cpu-baseline --no-tp-extra --steps 64 --warmup 8 2>/dev/null | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())
-print('variant[$sfx] rep $rep', d['value'], 'tok/s', d['ms_per_step'], 'ms', 'e2e', d['e2e']['value'])" >> gpurun_out/r2_ab_final32.log 2>&1
+print('variant[$sfx] rep $rep', d['value'], 'tok/s', d['ms_per_step'], 'ms', 'e2e', d['e2e']['value'])" >> gpurun_out/r2_ab_xprod_h2.log 2>&1
 done; done
