@@ -110,18 +110,15 @@ __device__ __forceinline__ void xp_had_warp128(float (&y)[4]) {
 // outputs are scaled, rounded to fp16 and stored in the B-fragment order of stage_x(): element i = 32*kh + pp lands in half
 // ((kh*16 + q*4 + kl*2 + b) << 1) | e with kl = pp >> 4, b = (pp >> 3) & 1, q = (pp >> 1) & 3, e = pp & 1 -- a permutation inside
 // each block of 32, so a thread's 32 results (stride >= 128 apart) share the in-block position.  No trailing barrier.
-__device__ __forceinline__ void xp_final32_stage(float *v, uint32_t *xs, int n, int lh, const XProd &p) {
-    const int lm = 31 - __clz(n);
-    while (lm - lh > 5) {  // n > 4096: bring the remaining strides down to five
-        if (lm - lh >= 8) fwht_pass<3>(v, n, lh), lh += 3;
-        else if (lm - lh == 7) fwht_pass<2>(v, n, lh), lh += 2;
-        else fwht_pass<1>(v, n, lh), lh += 1;
-        __syncthreads();
-    }
-    __half *xh = reinterpret_cast<__half *>(xs);
-    __half *xo = (p.x_out && blockIdx.x == 0) ? p.x_out : nullptr;
+// FIXED: the pass starts at stride 2^7 with n = 4096 known at compile time (the Llama-8B case: every address offset is an
+// immediate); WITH_XO: CTA 0 also stores x in natural order -- a separate instantiation, so that the other 147 CTAs do not issue 32
+// predicated-off global stores and their address arithmetic (this pass runs on 4 warps while the other 20 wait at the barrier)
+template <bool FIXED, bool WITH_XO>
+__device__ __forceinline__ void xp_final32_pass(const float *v, __half *xh, __half *xo, int n, int lh_rt, float scale) {
+    const int lh = FIXED ? 7 : lh_rt;
+    const int cnt = FIXED ? 128 : (n >> 5);
     const int h = 1 << lh;
-    for (int idx = threadIdx.x; idx < (n >> 5); idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
         const int low = idx & (h - 1), hi = idx >> lh;
         const int i0 = (hi << (5 + lh)) | low;
         float r[32];
@@ -142,11 +139,25 @@ __device__ __forceinline__ void xp_final32_stage(float *v, uint32_t *xs, int n, 
         const int d0 = ((((i0 >> 5) << 4) + (((pp >> 1) & 3) << 2) + ((pp >> 4) << 1) + ((pp >> 3) & 1)) << 1) | (pp & 1);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const __half o = __float2half_rn(r[k] * p.had_scale);
+            const __half o = __float2half_rn(r[k] * scale);
             xh[d0 + (k << lh)] = o;
-            if (xo) xo[i0 + (k << lh)] = o;
+            if (WITH_XO) xo[i0 + (k << lh)] = o;
         }
     }
+}
+
+__device__ __forceinline__ void xp_final32_stage(float *v, uint32_t *xs, int n, int lh, const XProd &p) {
+    const int lm = 31 - __clz(n);
+    while (lm - lh > 5) {  // n > 4096: bring the remaining strides down to five
+        if (lm - lh >= 8) fwht_pass<3>(v, n, lh), lh += 3;
+        else if (lm - lh == 7) fwht_pass<2>(v, n, lh), lh += 2;
+        else fwht_pass<1>(v, n, lh), lh += 1;
+        __syncthreads();
+    }
+    __half *xh = reinterpret_cast<__half *>(xs);
+    if (p.x_out && blockIdx.x == 0) xp_final32_pass<false, true>(v, xh, p.x_out, n, lh, p.had_scale);
+    else if (n == 4096) xp_final32_pass<true, false>(v, xh, nullptr, n, lh, p.had_scale);
+    else xp_final32_pass<false, false>(v, xh, nullptr, n, lh, p.had_scale);
 }
 
 __device__ __forceinline__ void xp_zero_slice(float *p, int count) {
