@@ -115,19 +115,29 @@ __device__ __forceinline__ void xp_had_warp128(float (&y)[4]) {
 // predicated-off global stores and their address arithmetic (this pass runs on 4 warps while the other 20 wait at the barrier)
 template <bool FIXED, bool WITH_XO>
 __device__ __forceinline__ void xp_final32_pass(const float *v, __half *xh, __half *xo, int n, int lh_rt, float scale) {
+    // Two threads per column set: both read the 32 inputs, the top stride is done first and each keeps one half of its results
+    // (sums or differences, warp-uniform), then finishes 16 values.  A single warp per scheduler runs this dependent chain at
+    // about a third of the issue rate (measured: 170 instructions fewer on this path were worth 0.28 us per launch), so two
+    // shorter chains on 8 warps beat one long chain on 4.  (The top stride first instead of last: same transform, fp32 sums in
+    // a different order than the stand-alone Hadamard kernel -- a 1e-7 effect, three orders below the run-to-run noise of the
+    // accumulators it is applied to.)
     const int lh = FIXED ? 7 : lh_rt;
-    const int cnt = FIXED ? 128 : (n >> 5);
+    const int lcnt = FIXED ? 7 : (31 - __clz(n)) - 5;  // log2 of the number of column sets
     const int h = 1 << lh;
-    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
+    unsigned short *xh16 = reinterpret_cast<unsigned short *>(xh);
+    unsigned short *xo16 = reinterpret_cast<unsigned short *>(xo);
+    for (int w = threadIdx.x; w < (2 << lcnt); w += blockDim.x) {
+        const int idx = w & ((1 << lcnt) - 1), half = w >> lcnt;
+        const float sg = half ? -1.f : 1.f;
         const int low = idx & (h - 1), hi = idx >> lh;
         const int i0 = (hi << (5 + lh)) | low;
-        float r[32];
+        float r[16];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = v[i0 + (k << lh)];
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(v[i0 + ((k + 16) << lh)], sg, v[i0 + (k << lh)]);
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
+        for (int s = 1; s < 16; s <<= 1) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 if ((k & s) == 0) {
                     const float a = r[k], b = r[k | s];
                     r[k] = a + b;
@@ -135,13 +145,14 @@ __device__ __forceinline__ void xp_final32_pass(const float *v, __half *xh, __ha
                 }
             }
         }
-        const int pp = i0 & 31;
-        const int d0 = ((((i0 >> 5) << 4) + (((pp >> 1) & 3) << 2) + ((pp >> 4) << 1) + ((pp >> 3) & 1)) << 1) | (pp & 1);
+        const int i1 = i0 + (half << (4 + lh));
+        const int pp = i1 & 31;
+        const int d0 = ((((i1 >> 5) << 4) + (((pp >> 1) & 3) << 2) + ((pp >> 4) << 1) + ((pp >> 3) & 1)) << 1) | (pp & 1);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const __half o = __float2half_rn(r[k] * scale);
-            xh[d0 + (k << lh)] = o;
-            if (WITH_XO) xo[i0 + (k << lh)] = o;
+        for (int k = 0; k < 16; ++k) {
+            const unsigned short o = __half_as_ushort(__float2half_rn(r[k] * scale));
+            xh16[d0 + (k << lh)] = o;
+            if (WITH_XO) xo16[i1 + (k << lh)] = o;
         }
     }
 }
